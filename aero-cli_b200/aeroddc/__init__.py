@@ -1,0 +1,185 @@
+"""aeroddc - thin ctypes binding of the C ABI in include/aeroddc.h (libaeroddc.so).
+
+This package is plumbing only: it loads the CUDA library built from aero-cli_b200/csrc and exposes
+the bank the way the reference drives its `vfo` objects (/root/reference/publish/vfo.h:16-40,
+publisher.cpp:118-148,159-219,301-305). There is no CPU implementation behind it: if the shared
+library is missing or no CUDA device is present, construction raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libaeroddc.so")
+
+CU8, CS16, CF32 = 0, 1, 2
+_NP_DTYPE = {CU8: np.uint8, CS16: np.int16, CF32: np.float32}
+
+
+class AeroDdcError(RuntimeError):
+    pass
+
+
+class VfoDesc(ctypes.Structure):
+    _fields_ = [
+        ("mixer_freq", ctypes.c_double),
+        ("decim_count", ctypes.c_int),
+        ("late_decimate", ctypes.c_int),
+        ("filter_bw", ctypes.c_int),
+        ("gain", ctypes.c_float),
+        ("demod_usb", ctypes.c_int),
+        ("compress_style", ctypes.c_int),
+        ("scale_comp", ctypes.c_int),
+        ("topic", ctypes.c_char * 64),
+    ]
+
+
+# every symbol include/aeroddc.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "aeroddc_bank_create", "aeroddc_bank_add_vfo", "aeroddc_bank_finalize", "aeroddc_bank_process",
+    "aeroddc_bank_submit", "aeroddc_bank_wait", "aeroddc_bank_host_slot", "aeroddc_bank_submit_device",
+    "aeroddc_bank_output", "aeroddc_bank_topic", "aeroddc_bank_stage_d", "aeroddc_bank_num_vfos",
+    "aeroddc_bank_last_timing", "aeroddc_bank_last_main_ms", "aeroddc_bank_device_bytes",
+    "aeroddc_bank_destroy", "aeroddc_last_error", "aeroddc_measure_fp32_peak", "aeroddc_abi_version",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libaeroddc.so; raises AeroDdcError if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AeroDdcError("%s not found: build it with `make -C aero-cli_b200/csrc` "
+                               "(or __graft_entry__.build()); there is no CPU fallback" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        vp, ci, cz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+        L.aeroddc_bank_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci]
+        L.aeroddc_bank_add_vfo.argtypes = [vp, ctypes.POINTER(VfoDesc)]
+        L.aeroddc_bank_finalize.argtypes = [vp]
+        L.aeroddc_bank_process.argtypes = [vp, vp, cz]
+        L.aeroddc_bank_submit.argtypes = [vp, vp, cz]
+        L.aeroddc_bank_wait.argtypes = [vp]
+        L.aeroddc_bank_host_slot.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(cz)]
+        L.aeroddc_bank_submit_device.argtypes = [vp, vp, cz, vp]
+        L.aeroddc_bank_output.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(cz), ctypes.POINTER(ctypes.c_uint32)]
+        L.aeroddc_bank_topic.argtypes = [vp, ci]
+        L.aeroddc_bank_topic.restype = ctypes.c_char_p
+        L.aeroddc_bank_stage_d.argtypes = [vp, ci, vp, cz]
+        L.aeroddc_bank_num_vfos.argtypes = [vp]
+        L.aeroddc_bank_last_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ci)]
+        L.aeroddc_bank_last_main_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+        L.aeroddc_bank_device_bytes.argtypes = [vp, ctypes.POINTER(cz)]
+        L.aeroddc_bank_destroy.argtypes = [vp]
+        L.aeroddc_bank_destroy.restype = None
+        L.aeroddc_last_error.restype = ctypes.c_char_p
+        L.aeroddc_measure_fp32_peak.argtypes = [ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc < 0:
+        raise AeroDdcError("aeroddc error %d: %s" % (rc, lib().aeroddc_last_error().decode()))
+    return rc
+
+
+def measure_fp32_peak(device=0):
+    """(TFLOP/s counting FMA as 2, SM clock in MHz) from the library's FFMA issue-rate probe."""
+    t, c = ctypes.c_double(), ctypes.c_double()
+    _check(lib().aeroddc_measure_fp32_peak(device, ctypes.byref(t), ctypes.byref(c)))
+    return t.value, c.value
+
+
+class Bank:
+    """All VFOs of one raw-IQ stream. Mirrors create -> add_vfo* -> finalize -> process* of the ABI."""
+
+    def __init__(self, sample_rate, block_len, in_format=CF32, device=0):
+        self._L = lib()
+        self._h = ctypes.c_void_p()
+        self.sample_rate, self.block_len, self.in_format, self.device = sample_rate, block_len, in_format, device
+        _check(self._L.aeroddc_bank_create(ctypes.byref(self._h), sample_rate, block_len, in_format, device))
+
+    def add_vfo(self, mixer_freq, decim_count, late_decimate=0, filter_bw=0, gain=0.01, demod_usb=1,
+                compress_style=1, scale_comp=1, topic=""):
+        d = VfoDesc(float(mixer_freq), int(decim_count), int(late_decimate), int(filter_bw), float(gain),
+                    int(demod_usb), int(compress_style), int(scale_comp), topic.encode()[:63])
+        return _check(self._L.aeroddc_bank_add_vfo(self._h, ctypes.byref(d)))
+
+    def finalize(self):
+        _check(self._L.aeroddc_bank_finalize(self._h))
+
+    @property
+    def num_vfos(self):
+        return self._L.aeroddc_bank_num_vfos(self._h)
+
+    def _ptr(self, block):
+        if isinstance(block, np.ndarray):
+            if block.dtype != _NP_DTYPE[self.in_format] or not block.flags.c_contiguous:
+                raise AeroDdcError("block must be a C-contiguous %s array" % _NP_DTYPE[self.in_format].__name__)
+            if block.size != 2 * self.block_len:
+                raise AeroDdcError("block has %d values, expected %d" % (block.size, 2 * self.block_len))
+            return block.ctypes.data
+        return int(block)
+
+    def process(self, block):
+        _check(self._L.aeroddc_bank_process(self._h, self._ptr(block), self.block_len))
+
+    def submit(self, block):
+        _check(self._L.aeroddc_bank_submit(self._h, self._ptr(block), self.block_len))
+
+    def submit_device(self, dev_ptr, ready_event=None):
+        _check(self._L.aeroddc_bank_submit_device(self._h, int(dev_ptr), self.block_len, ready_event))
+
+    def wait(self):
+        _check(self._L.aeroddc_bank_wait(self._h))
+
+    def host_slot(self, slot):
+        """numpy view of pinned staging slot 0/1 (dtype of the input format, 2*block_len values)."""
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        _check(self._L.aeroddc_bank_host_slot(self._h, slot, ctypes.byref(p), ctypes.byref(n)))
+        dt = np.dtype(_NP_DTYPE[self.in_format])
+        buf = (ctypes.c_ubyte * n.value).from_address(p.value)
+        return np.frombuffer(buf, dtype=dt)
+
+    def output(self, vfo):
+        """(payload bytes, output rate) of the most recently completed block."""
+        p, n, r = ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_uint32()
+        _check(self._L.aeroddc_bank_output(self._h, vfo, ctypes.byref(p), ctypes.byref(n), ctypes.byref(r)))
+        return ctypes.string_at(p.value, n.value), r.value
+
+    def topic(self, vfo):
+        return self._L.aeroddc_bank_topic(self._h, vfo).decode()
+
+    def stage_d(self, vfo, n_complex):
+        out = np.empty(2 * n_complex, np.float32)
+        n = _check(self._L.aeroddc_bank_stage_d(self._h, vfo, out.ctypes.data, n_complex))
+        return out[: 2 * min(n, n_complex)]
+
+    def last_timing(self):
+        ms, n = ctypes.c_float(), ctypes.c_int()
+        _check(self._L.aeroddc_bank_last_timing(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
+    def last_main_ms(self):
+        ms = ctypes.c_float()
+        _check(self._L.aeroddc_bank_last_main_ms(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    def device_bytes(self):
+        n = ctypes.c_size_t()
+        _check(self._L.aeroddc_bank_device_bytes(self._h, ctypes.byref(n)))
+        return n.value
+
+    def close(self):
+        if self._h:
+            self._L.aeroddc_bank_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

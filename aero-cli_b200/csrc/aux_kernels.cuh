@@ -1,0 +1,218 @@
+// aero-ddc-b200: the small kernels around the main cascade kernel.
+//   nco_checkpoint_kernel : Oscillator::Oscillator table recurrence   oscillator.cpp:12-27
+//   tail_kernel           : usb_demod / usb_decimdemod / compress     vfo.cpp:188-287
+//                           FIR::FIRUpdateAndProcess, FIRHilbert, DelayThing   dsp.cpp:64-78,216-231, dsp.h:74-96
+//   fp32_peak_kernel      : register-only FFMA issue-rate probe (roofline denominator)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace aeroddc {
+
+// ---------------------------------------------------------------------------------------------
+// NCO checkpoints. One thread per VFO walks the reference recurrence v *= rot; v *= 1.95f - |v|^2
+// for L steps in un-fused float arithmetic (scalar __fmul_rn/__fadd_rn are never contracted) and
+// stores the state after every `stride` steps: ckpt[k][v] = state after k*stride steps (k = 0 is
+// (1,0)), i.e. the value from which one more step yields table entry q[k*stride]. qlast = q[L-1].
+// ---------------------------------------------------------------------------------------------
+__global__ void nco_checkpoint_kernel(const float2* __restrict__ rot, float2* __restrict__ ckpt,
+                                      float2* __restrict__ qlast, int n_vfo, int vfo_pitch, int L, int stride) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_vfo) return;
+  const float c = rot[v].x, d = rot[v].y;
+  float a = 1.0f, b = 0.0f;
+  int k = 0;
+  for (int i = 0; i < L; i += stride) {
+    ckpt[(size_t)k * vfo_pitch + v] = make_float2(a, b);
+    ++k;
+    const int n = min(stride, L - i);
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) {
+      const float nr = __fsub_rn(__fmul_rn(a, c), __fmul_rn(b, d));
+      const float ni = __fadd_rn(__fmul_rn(a, d), __fmul_rn(b, c));
+      const float nm = __fsub_rn(1.95f, __fadd_rn(__fmul_rn(nr, nr), __fmul_rn(ni, ni)));
+      a = __fmul_rn(nr, nm);
+      b = __fmul_rn(ni, nm);
+    }
+  }
+  qlast[v] = make_float2(a, b);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tail. Stateless given the stage-D stream with enough history in front of the block:
+//   m[k] = late > 0 ? sum_{i<T} tl[i] * xD[k*late - T + i] : xD[k]        (newest sample excluded)
+//   u[k] = Re m[k-62] - sum_{i<125} hil[i] * Im m[k-124+i]                (newest included)
+//   y[k] = U > 0 ? sum_{i<U} tu[i] * u[k-U+i] : u[k]                      (newest excluded)
+//   out[k] = (short) trunc(double(y[k] * gain) * 32768.0)
+// every sum accumulated left to right from 0.0f with separately rounded products.
+// ---------------------------------------------------------------------------------------------
+struct TailVfo {
+  const float2* xd;      // points at stage-D index 0 of this block; negative indices are history
+  unsigned char* out;    // payload row
+  const float* late_taps;
+  const float* usb_taps;
+  const float* hil_taps;
+  int n_stage, n_out;
+  int late, T, U;
+  int demod_usb, cstyle, scalecomp;
+  float gain;
+};
+
+constexpr int kTailChunk = 512;
+constexpr int kTailThreads = 256;
+constexpr int kHilbert = 125;
+constexpr int kDelay = 62;
+
+__device__ __forceinline__ short to_short_x86(float g) {
+  // double(g) * 32768.0 is exact; conversion truncates toward zero; out of int32 range x86 yields
+  // INT_MIN whose low 16 bits are 0 (the C++ conversion is undefined there; the oracle pins the same)
+  const double v = (double)g * 32768.0;
+  int i;
+  if (!(v > -2147483649.0 && v < 2147483648.0)) i = (int)0x80000000;
+  else i = __double2int_rz(v);
+  return (short)(unsigned short)((unsigned)i & 0xFFFFu);
+}
+__device__ __forceinline__ int to_schar_x86(float v) {
+  int i;
+  if (!(v > -2147483904.0f && v < 2147483648.0f)) i = (int)0x80000000;
+  else i = __float2int_rz(v);
+  return (int)(signed char)(unsigned char)((unsigned)i & 0xFFu);
+}
+
+__global__ void __launch_bounds__(kTailThreads) tail_kernel(const TailVfo* __restrict__ vfos) {
+  extern __shared__ __align__(16) unsigned char tsm[];
+  const TailVfo v = vfos[blockIdx.y];
+  const int k0 = blockIdx.x * kTailChunk;
+  if (k0 >= v.n_out) return;
+  const int kc = min(kTailChunk, v.n_out - k0);
+  const int tid = threadIdx.x;
+
+  if (!v.demod_usb) {   // vfo::compress (vfo.cpp:260-287)
+    for (int k = tid; k < kc; k += kTailThreads) {
+      const float2 s = v.xd[k0 + k];
+      if (v.cstyle == 1) {
+        const float sc = (float)v.scalecomp;
+        const int re = to_schar_x86(__fmul_rn(__fdiv_rn(s.x, sc), 128.0f));
+        const int im = to_schar_x86(__fmul_rn(__fdiv_rn(s.y, sc), 128.0f));
+        v.out[k0 + k] = (unsigned char)((re & 0xF0) | ((im & 0xF0) >> 4));
+      } else {
+        v.out[2 * (k0 + k)] = (unsigned char)to_schar_x86(__fmul_rn(s.x, 128.0f));
+        v.out[2 * (k0 + k) + 1] = (unsigned char)to_schar_x86(__fmul_rn(s.y, 128.0f));
+      }
+    }
+    return;
+  }
+
+  // shared layout: m[(kHilbert-1) + U + kc] float2 | u[U + kc] float | taps
+  const int n_m = (kHilbert - 1) + v.U + kc;
+  const int n_u = v.U + kc;
+  float2* m = reinterpret_cast<float2*>(tsm);
+  float* u = reinterpret_cast<float*>(m + n_m);
+  float* tl = u + n_u;
+  float* tu = tl + v.T;
+  float* th = tu + v.U;
+  for (int i = tid; i < v.T; i += kTailThreads) tl[i] = v.late_taps[i];
+  for (int i = tid; i < v.U; i += kTailThreads) tu[i] = v.usb_taps[i];
+  for (int i = tid; i < kHilbert; i += kTailThreads) th[i] = v.hil_taps[i];
+  __syncthreads();
+
+  // phase 1: m[j] for k = k0 - U - 124 + j
+  const int kbase = k0 - v.U - (kHilbert - 1);
+  for (int j = tid; j < n_m; j += kTailThreads) {
+    const int k = kbase + j;
+    if (v.late > 0) {
+      const float2* w = v.xd + ((long long)k * v.late - v.T);
+      float ar = 0.0f, ai = 0.0f;
+      for (int i = 0; i < v.T; ++i) {
+        const float2 s = w[i];
+        ar = __fadd_rn(ar, __fmul_rn(tl[i], s.x));
+        ai = __fadd_rn(ai, __fmul_rn(tl[i], s.y));
+      }
+      m[j] = make_float2(ar, ai);
+    } else {
+      m[j] = v.xd[k];
+    }
+  }
+  __syncthreads();
+  // phase 2: u[j] for k = k0 - U + j ; m index of k is k - kbase = j + 124
+  for (int j = tid; j < n_u; j += kTailThreads) {
+    const int mi = j + (kHilbert - 1);
+    float h = 0.0f;
+    const float2* w = m + (mi - (kHilbert - 1));
+#pragma unroll 5
+    for (int i = 0; i < kHilbert; ++i) h = __fadd_rn(h, __fmul_rn(th[i], w[i].y));
+    u[j] = __fsub_rn(m[mi - kDelay].x, h);
+  }
+  __syncthreads();
+  // phase 3
+  short* o16 = reinterpret_cast<short*>(v.out);
+  for (int k = tid; k < kc; k += kTailThreads) {
+    float y;
+    if (v.U > 0) {
+      const float* w = u + k;   // u index of output k0+k is k + U; window starts U earlier
+      y = 0.0f;
+      for (int i = 0; i < v.U; ++i) y = __fadd_rn(y, __fmul_rn(tu[i], w[i]));
+    } else {
+      y = u[k];
+    }
+    o16[k0 + k] = to_short_x86(__fmul_rn(y, v.gain));
+  }
+}
+
+// Keep the last `hist` stage-D samples of every VFO in front of its next block: row[i] = row[n_stage + i],
+// i < hist. Source and destination overlap when n_stage < hist; moving forward in chunks with the
+// whole chunk read before any of it is written keeps that safe (dst < src).
+__global__ void __launch_bounds__(256) xd_shift_kernel(const TailVfo* __restrict__ vfos, int hist) {
+  const TailVfo v = vfos[blockIdx.x];
+  float2* row = const_cast<float2*>(v.xd) - hist;
+  for (int base = 0; base < hist; base += 1024) {
+    float2 r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = base + j * 256 + threadIdx.x;
+      if (i < hist) r[j] = row[v.n_stage + i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = base + j * 256 + threadIdx.x;
+      if (i < hist) row[i] = r[j];
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP32 peak probe: 8 independent FFMA2 chains per thread, 64 resident warps per SM.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float m, float c, long long* clk) {
+  unsigned long long p[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float a = threadIdx.x * 0.001f + i;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(p[i]) : "f"(a), "f"(a + 0.5f));
+  }
+  unsigned long long pm, pc;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(pm) : "f"(m));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(pc) : "f"(c));
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(pm), "l"(pc));
+    }
+  }
+  const long long t1 = clock64();
+  float r = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p[i]));
+    r += a + b;
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+  if (threadIdx.x == 0 && blockIdx.x == 0) clk[0] = t1 - t0;
+}
+
+}  // namespace aeroddc

@@ -1,0 +1,573 @@
+// aero-ddc-b200: the bank object behind the C ABI of include/aeroddc.h.
+//
+// Host orchestration only: VFO bookkeeping, host-side filter design (design.cpp), HBM layout,
+// streams/events, and the launches of the kernels in ddc_kernels.cuh / aux_kernels.cuh.
+// Replaces the per-VFO objects of /root/reference/publish/vfo.cpp:57-139 (init) and the block pump
+// of /root/reference/publish/publisher.cpp:285-306 (demodData -> vfo::process for every VFO).
+#include "../../include/aeroddc.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "ddc_kernels.cuh"
+#include "design.h"
+
+namespace {
+
+thread_local std::string t_err;
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  t_err = buf;
+  return code;
+}
+#define CU(x)                                                                                            \
+  do {                                                                                                   \
+    cudaError_t e_ = (x);                                                                                \
+    if (e_ != cudaSuccess) return fail(AERODDC_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+using namespace aeroddc;
+
+struct VfoRec {
+  aeroddc_vfo_desc d;
+  TailPlan plan;
+  int slot;          // column in the device tables (VFOs are grouped by decimation count)
+  int hist;          // stage-D history samples kept in front of each block
+  size_t out_bytes;  // payload bytes per block
+  size_t out_off;    // offset of the payload row in the output buffers
+  size_t taps_off[3];
+};
+
+struct Group {   // VFOs sharing D: one launch of the main kernel per block
+  int D, base, count;
+  int S, W, Wb, nseg;
+};
+
+int raw_bytes(int fmt) { return fmt == AERODDC_CU8 ? 2 : (fmt == AERODDC_CS16 ? 4 : 8); }
+
+int ilcm(int a, int b) {
+  int x = a, y = b;
+  while (y) { int t = x % y; x = y; y = t; }
+  return a / x * b;
+}
+
+}  // namespace
+
+struct aeroddc_bank {
+  int fs = 0, B = 0, fmt = 0, device = 0;
+  bool finalized = false;
+  std::vector<VfoRec> vfos;
+  std::vector<Group> groups;
+  int vfo_pitch = 0;
+  int n_sm = 148;
+  int nck = 0;
+
+  // device memory
+  float2 *d_rot = nullptr, *d_qlast = nullptr, *d_ckpt = nullptr;
+  float2* d_state[2] = {nullptr, nullptr};
+  float2* d_xd = nullptr;       // [vfo_pitch][xd_pitch]
+  int xd_pitch = 0, hist_max = 0, nstage_max = 0;
+  float* d_taps = nullptr;
+  TailVfo* d_tail = nullptr;
+  unsigned char* d_out = nullptr;
+  size_t out_total = 0;
+  unsigned char* d_in[2] = {nullptr, nullptr};
+  size_t in_bytes = 0;
+  size_t dev_bytes = 0;
+
+  // host memory
+  unsigned char* h_in[2] = {nullptr, nullptr};
+  unsigned char* h_out[3] = {nullptr, nullptr, nullptr};   // three slots: a payload stays valid until the next wait()
+
+  cudaStream_t s_compute = nullptr, s_copy = nullptr;
+  cudaEvent_t ev_h2d[2] = {};
+  cudaEvent_t ev_done[3] = {}, ev_k0[3] = {}, ev_k1[3] = {}, ev_m0[3] = {}, ev_m1[3] = {};
+
+  long long blocks_submitted = 0, blocks_done = 0;
+  int cur_out = -1;   // h_out slot returned by output()
+  float last_kernel_ms = 0, last_main_ms = 0;
+  int last_launches = 0;
+  int launches_per_block = 0;
+  size_t tail_smem = 0;
+  int tail_chunks = 0;
+};
+
+namespace {
+
+template <int NF, int FMT>
+cudaError_t launch_main_t(const MainParams& p, dim3 grid, cudaStream_t s) {
+  const int smem = TileSmem<FMT>::kTotal;
+  cudaError_t e = cudaFuncSetAttribute(ddc_main_kernel<NF, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  ddc_main_kernel<NF, FMT><<<grid, kThreads, smem, s>>>(p);
+  return cudaGetLastError();
+}
+template <int FMT>
+cudaError_t launch_main_f(int nf, const MainParams& p, dim3 grid, cudaStream_t s) {
+  switch (nf) {
+    case 0: return launch_main_t<0, FMT>(p, grid, s);
+    case 1: return launch_main_t<1, FMT>(p, grid, s);
+    case 2: return launch_main_t<2, FMT>(p, grid, s);
+    case 3: return launch_main_t<3, FMT>(p, grid, s);
+    default: return launch_main_t<4, FMT>(p, grid, s);
+  }
+}
+cudaError_t launch_main(int fmt, int nf, const MainParams& p, dim3 grid, cudaStream_t s) {
+  if (fmt == AERODDC_CU8) return launch_main_f<FMT_CU8>(nf, p, grid, s);
+  if (fmt == AERODDC_CS16) return launch_main_f<FMT_CS16>(nf, p, grid, s);
+  return launch_main_f<FMT_CF32>(nf, p, grid, s);
+}
+
+void free_all(aeroddc_bank* b) {
+  cudaSetDevice(b->device);
+  if (b->s_compute) cudaStreamSynchronize(b->s_compute);
+  if (b->s_copy) cudaStreamSynchronize(b->s_copy);
+  cudaFree(b->d_rot); cudaFree(b->d_qlast); cudaFree(b->d_ckpt);
+  cudaFree(b->d_state[0]); cudaFree(b->d_state[1]);
+  cudaFree(b->d_xd); cudaFree(b->d_taps); cudaFree(b->d_tail); cudaFree(b->d_out);
+  cudaFree(b->d_in[0]); cudaFree(b->d_in[1]);
+  for (int i = 0; i < 2; ++i) {
+    if (b->h_in[i]) cudaFreeHost(b->h_in[i]);
+    if (b->ev_h2d[i]) cudaEventDestroy(b->ev_h2d[i]);
+  }
+  for (int i = 0; i < 3; ++i) {
+    if (b->h_out[i]) cudaFreeHost(b->h_out[i]);
+    if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]);
+    if (b->ev_k0[i]) cudaEventDestroy(b->ev_k0[i]);
+    if (b->ev_k1[i]) cudaEventDestroy(b->ev_k1[i]);
+    if (b->ev_m0[i]) cudaEventDestroy(b->ev_m0[i]);
+    if (b->ev_m1[i]) cudaEventDestroy(b->ev_m1[i]);
+  }
+  if (b->s_compute) cudaStreamDestroy(b->s_compute);
+  if (b->s_copy) cudaStreamDestroy(b->s_copy);
+}
+
+// enqueue everything that follows the arrival of the raw block in device memory
+int enqueue_block(aeroddc_bank* b, const void* dev_iq) {
+  const int slot = (int)(b->blocks_submitted % 3);   // payload/event slot
+  cudaStream_t s = b->s_compute;
+  const long long block_abs = b->blocks_submitted * (long long)b->B;
+  const int par = (int)(b->blocks_submitted & 1);
+  int launches = 0;
+  CU(cudaEventRecord(b->ev_k0[slot], s));
+  CU(cudaEventRecord(b->ev_m0[slot], s));
+  for (const Group& g : b->groups) {
+    MainParams p;
+    p.iq = dev_iq;
+    p.ckpt = b->d_ckpt;
+    p.rot = b->d_rot;
+    p.qlast = b->d_qlast;
+    p.state_in = b->d_state[par];
+    p.state_out = b->d_state[par ^ 1];
+    p.xd = b->d_xd;
+    p.block_abs = block_abs;
+    p.xd_pitch = b->xd_pitch;
+    p.xd_hist = b->hist_max;
+    p.vfo_pitch = b->vfo_pitch;
+    p.vfo_base = g.base;
+    p.vfo_count = g.count;
+    p.D = g.D;
+    p.B = b->B;
+    p.S = g.S;
+    p.W = g.W;
+    p.nseg = g.nseg;
+    p.Wb = g.Wb;
+    p.nco_len = b->fs;
+    p.one = 1.0f;
+    p.mone = -1.0f;
+    dim3 grid(g.nseg + 1, (g.count + kVfoPerCta - 1) / kVfoPerCta);
+    CU(launch_main(b->fmt, std::min(g.D, kFastStages), p, grid, s));
+    ++launches;
+  }
+  CU(cudaEventRecord(b->ev_m1[slot], s));
+  {
+    dim3 grid(b->tail_chunks, (unsigned)b->vfos.size());
+    tail_kernel<<<grid, kTailThreads, b->tail_smem, s>>>(b->d_tail);
+    CU(cudaGetLastError());
+    ++launches;
+  }
+  CU(cudaEventRecord(b->ev_k1[slot], s));
+  // keep the last hist_max stage-D samples of every VFO in front of the next block
+  if (b->hist_max > 0) {
+    xd_shift_kernel<<<(unsigned)b->vfos.size(), 256, 0, s>>>(b->d_tail, b->hist_max);
+    CU(cudaGetLastError());
+    ++launches;
+  }
+  CU(cudaMemcpyAsync(b->h_out[slot], b->d_out, b->out_total, cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(b->ev_done[slot], s));
+  b->launches_per_block = launches;
+  b->blocks_submitted++;
+  return AERODDC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int aeroddc_abi_version(void) { return AERODDC_ABI_VERSION; }
+const char* aeroddc_last_error(void) { return t_err.c_str(); }
+
+int aeroddc_bank_create(aeroddc_bank** out, int sample_rate, int block_len, int in_format, int device) {
+  if (!out) return fail(AERODDC_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (sample_rate <= 0 || block_len <= 0) return fail(AERODDC_ERR_ARG, "sample_rate and block_len must be positive");
+  if (block_len > sample_rate)
+    return fail(AERODDC_ERR_ARG, "block_len %d > sample_rate %d: the reference's half-band queue holds inlen+11 samples (dsp.cpp:43)",
+                block_len, sample_rate);
+  if (in_format < AERODDC_CU8 || in_format > AERODDC_CF32) return fail(AERODDC_ERR_ARG, "unknown input format %d", in_format);
+  if (block_len % kChunk) return fail(AERODDC_ERR_ARG, "block_len must be a multiple of %d", kChunk);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(AERODDC_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(AERODDC_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+  aeroddc_bank* b = new (std::nothrow) aeroddc_bank();
+  if (!b) return fail(AERODDC_ERR_NOMEM, "out of host memory");
+  b->fs = sample_rate;
+  b->B = block_len;
+  b->fmt = in_format;
+  b->device = device;
+  *out = b;
+  return AERODDC_OK;
+}
+
+int aeroddc_bank_add_vfo(aeroddc_bank* b, const aeroddc_vfo_desc* d) {
+  if (!b || !d) return fail(AERODDC_ERR_ARG, "NULL argument");
+  if (b->finalized) return fail(AERODDC_ERR_STATE, "bank already finalized");
+  if (d->decim_count < 0 || d->decim_count > kMaxStages)
+    return fail(AERODDC_ERR_ARG, "decim_count %d outside 0..8 (vfo.h:63)", d->decim_count);
+  const int step = ilcm(kChunk, 1 << d->decim_count);
+  if (b->B % step) return fail(AERODDC_ERR_ARG, "block_len %d not a multiple of %d for D=%d", b->B, step, d->decim_count);
+  if (d->decim_count > 0 && b->B < 20 * (1 << d->decim_count))
+    return fail(AERODDC_ERR_ARG, "block_len %d too short for D=%d (need >= %d)", b->B, d->decim_count, 20 << d->decim_count);
+  const int late = d->demod_usb ? d->late_decimate : 0;
+  if (late < 0 || late == 1) return fail(AERODDC_ERR_ARG, "late_decimate must be 0 or >= 2");
+  const int n_stage = b->B >> d->decim_count;
+  if (late > 0 && n_stage % late) return fail(AERODDC_ERR_ARG, "stage-D block %d not divisible by late_decimate %d", n_stage, late);
+  VfoRec r;
+  r.d = *d;
+  r.d.topic[sizeof r.d.topic - 1] = 0;
+  if (r.d.scale_comp <= 0) r.d.scale_comp = 1;
+  if (!plan_tail(b->fs, b->B, d->decim_count, late, d->filter_bw, d->demod_usb != 0, &r.plan))
+    return fail(AERODDC_ERR_DESIGN, "filter design rejected (fs=%d D=%d late=%d bw=%d)", b->fs, d->decim_count, late, d->filter_bw);
+  if (r.plan.n_out < 1) return fail(AERODDC_ERR_ARG, "no output samples per block");
+  const int T = (int)r.plan.late_taps.size(), U = (int)r.plan.usb_taps.size();
+  if (U > 4096) return fail(AERODDC_ERR_ARG, "fir_usb with %d taps is not supported (max 4096)", U);
+  r.hist = d->demod_usb ? (U + kHilbert - 1) * std::max(late, 1) + T : 0;
+  r.out_bytes = d->demod_usb ? (size_t)r.plan.n_out * 2 : (d->compress_style == 1 ? (size_t)r.plan.n_out : (size_t)r.plan.n_out * 2);
+  b->vfos.push_back(r);
+  return (int)b->vfos.size() - 1;
+}
+
+int aeroddc_bank_finalize(aeroddc_bank* b) {
+  if (!b) return fail(AERODDC_ERR_ARG, "NULL bank");
+  if (b->finalized) return fail(AERODDC_ERR_STATE, "already finalized");
+  if (b->vfos.empty()) return fail(AERODDC_ERR_STATE, "no VFOs");
+  CU(cudaSetDevice(b->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, b->device));
+  if (prop.major < 10) return fail(AERODDC_ERR_CUDA, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+  b->n_sm = prop.multiProcessorCount;
+
+  // ---- group VFOs by D; each group starts at an even column ----
+  const int nv = (int)b->vfos.size();
+  int col = 0;
+  for (int D = 0; D <= kMaxStages; ++D) {
+    Group g;
+    g.D = D; g.base = col; g.count = 0;
+    for (int i = 0; i < nv; ++i)
+      if (b->vfos[i].d.decim_count == D) { b->vfos[i].slot = col++; g.count++; }
+    if (!g.count) continue;
+    if (col & 1) ++col;
+    b->groups.push_back(g);
+  }
+  b->vfo_pitch = (col + 3) & ~3;
+  const char* env_waves = getenv("AERODDC_WAVES");
+  const double waves = env_waves ? std::max(0.25, atof(env_waves)) : 1.0;
+  for (Group& g : b->groups) {
+    const int align = ilcm(kNcoStride, 1 << g.D);
+    g.W = g.D == 0 ? 0 : ((10 << g.D) + (ilcm(kChunk, 1 << g.D) - 1)) / ilcm(kChunk, 1 << g.D) * ilcm(kChunk, 1 << g.D);
+    g.Wb = g.D == 0 ? 0 : (11 << g.D);
+    const int nblk_y = (g.count + kVfoPerCta - 1) / kVfoPerCta;
+    const int target = std::max(1, (int)std::floor(2.0 * b->n_sm * waves / nblk_y) - 1);   // -1: the boundary CTA
+    int S = (b->B + target - 1) / target;
+    S = std::max(S, std::max(4 * g.W, 4096));
+    S = (S + align - 1) / align * align;
+    g.S = S;
+    g.nseg = (b->B + S - 1) / S;
+  }
+
+  // ---- constant tables ----
+  std::vector<float2> h_rot(b->vfo_pitch, make_float2(1.0f, 0.0f));
+  for (const VfoRec& r : b->vfos) design_rotation((double)b->fs, r.d.mixer_freq, &h_rot[r.slot].x, &h_rot[r.slot].y);
+  b->nck = (b->fs + kNcoStride - 1) / kNcoStride;
+  size_t bytes = 0;
+  auto dmalloc = [&](void** p, size_t n) { bytes += n; return cudaMalloc(p, n); };
+  CU(dmalloc((void**)&b->d_rot, sizeof(float2) * b->vfo_pitch));
+  CU(dmalloc((void**)&b->d_qlast, sizeof(float2) * b->vfo_pitch));
+  CU(dmalloc((void**)&b->d_ckpt, sizeof(float2) * (size_t)b->nck * b->vfo_pitch));
+  CU(cudaMemset(b->d_ckpt, 0, sizeof(float2) * (size_t)b->nck * b->vfo_pitch));
+  CU(cudaMemset(b->d_qlast, 0, sizeof(float2) * b->vfo_pitch));
+  CU(cudaMemcpy(b->d_rot, h_rot.data(), sizeof(float2) * b->vfo_pitch, cudaMemcpyHostToDevice));
+  for (int i = 0; i < 2; ++i) {
+    const size_t n = sizeof(float2) * (size_t)kMaxStages * kStateSlots * b->vfo_pitch;
+    CU(dmalloc((void**)&b->d_state[i], n));
+    CU(cudaMemset(b->d_state[i], 0, n));   // first block: all-zero history (dsp.cpp:48-52)
+  }
+
+  // ---- stage-D stream and payload rows ----
+  b->hist_max = 0; b->nstage_max = 0;
+  size_t taps_total = 0, out_off = 0;
+  for (VfoRec& r : b->vfos) {
+    b->hist_max = std::max(b->hist_max, r.hist);
+    b->nstage_max = std::max(b->nstage_max, r.plan.n_stage);
+    r.taps_off[0] = taps_total; taps_total += r.plan.late_taps.size();
+    r.taps_off[1] = taps_total; taps_total += r.plan.usb_taps.size();
+    r.taps_off[2] = taps_total; taps_total += r.plan.hilbert_taps.size();
+    r.out_off = out_off;
+    out_off += (r.out_bytes + 15) & ~(size_t)15;
+  }
+  b->hist_max = (b->hist_max + 1) & ~1;
+  b->out_total = out_off;
+  b->xd_pitch = ((b->hist_max + b->nstage_max + 1) & ~1);
+  CU(dmalloc((void**)&b->d_xd, sizeof(float2) * (size_t)b->vfo_pitch * b->xd_pitch));
+  CU(cudaMemset(b->d_xd, 0, sizeof(float2) * (size_t)b->vfo_pitch * b->xd_pitch));
+  std::vector<float> h_taps(std::max<size_t>(taps_total, 1));
+  for (const VfoRec& r : b->vfos) {
+    std::copy(r.plan.late_taps.begin(), r.plan.late_taps.end(), h_taps.begin() + r.taps_off[0]);
+    std::copy(r.plan.usb_taps.begin(), r.plan.usb_taps.end(), h_taps.begin() + r.taps_off[1]);
+    std::copy(r.plan.hilbert_taps.begin(), r.plan.hilbert_taps.end(), h_taps.begin() + r.taps_off[2]);
+  }
+  CU(dmalloc((void**)&b->d_taps, sizeof(float) * h_taps.size()));
+  CU(cudaMemcpy(b->d_taps, h_taps.data(), sizeof(float) * h_taps.size(), cudaMemcpyHostToDevice));
+  CU(dmalloc((void**)&b->d_out, b->out_total));
+  CU(cudaMemset(b->d_out, 0, b->out_total));
+  std::vector<TailVfo> h_tail(nv);
+  size_t tail_smem = 0;
+  int max_out = 0;
+  for (int i = 0; i < nv; ++i) {
+    const VfoRec& r = b->vfos[i];
+    TailVfo& t = h_tail[i];
+    t.xd = b->d_xd + (size_t)r.slot * b->xd_pitch + b->hist_max;
+    t.out = b->d_out + r.out_off;
+    t.late_taps = b->d_taps + r.taps_off[0];
+    t.usb_taps = b->d_taps + r.taps_off[1];
+    t.hil_taps = b->d_taps + r.taps_off[2];
+    t.n_stage = r.plan.n_stage;
+    t.n_out = r.plan.n_out;
+    t.late = r.plan.late;
+    t.T = (int)r.plan.late_taps.size();
+    t.U = (int)r.plan.usb_taps.size();
+    t.demod_usb = r.d.demod_usb != 0;
+    t.cstyle = r.d.compress_style;
+    t.scalecomp = r.d.scale_comp;
+    t.gain = r.d.gain;
+    max_out = std::max(max_out, t.n_out);
+    const size_t sm = sizeof(float2) * (kHilbert - 1 + t.U + kTailChunk) + sizeof(float) * (t.U + kTailChunk) +
+                      sizeof(float) * (t.T + t.U + kHilbert) + 16;
+    tail_smem = std::max(tail_smem, sm);
+  }
+  b->tail_smem = tail_smem;
+  b->tail_chunks = (max_out + kTailChunk - 1) / kTailChunk;
+  CU(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
+  CU(dmalloc((void**)&b->d_tail, sizeof(TailVfo) * nv));
+  CU(cudaMemcpy(b->d_tail, h_tail.data(), sizeof(TailVfo) * nv, cudaMemcpyHostToDevice));
+
+  // ---- input staging ----
+  b->in_bytes = (size_t)b->B * raw_bytes(b->fmt);
+  for (int i = 0; i < 2; ++i) {
+    CU(dmalloc((void**)&b->d_in[i], b->in_bytes));
+    CU(cudaHostAlloc((void**)&b->h_in[i], b->in_bytes, cudaHostAllocDefault));
+    CU(cudaEventCreateWithFlags(&b->ev_h2d[i], cudaEventDisableTiming));
+  }
+  for (int i = 0; i < 3; ++i) {
+    CU(cudaHostAlloc((void**)&b->h_out[i], std::max<size_t>(b->out_total, 16), cudaHostAllocDefault));
+    memset(b->h_out[i], 0, std::max<size_t>(b->out_total, 16));
+    CU(cudaEventCreate(&b->ev_k0[i])); CU(cudaEventCreate(&b->ev_k1[i]));
+    CU(cudaEventCreate(&b->ev_m0[i])); CU(cudaEventCreate(&b->ev_m1[i]));
+    CU(cudaEventCreateWithFlags(&b->ev_done[i], cudaEventDisableTiming));
+  }
+  CU(cudaStreamCreateWithFlags(&b->s_compute, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&b->s_copy, cudaStreamNonBlocking));
+
+  // ---- NCO checkpoints: the exact sequential recurrence, one thread per VFO ----
+  {
+    const int threads = 32;
+    nco_checkpoint_kernel<<<(b->vfo_pitch + threads - 1) / threads, threads, 0, b->s_compute>>>(
+        b->d_rot, b->d_ckpt, b->d_qlast, b->vfo_pitch, b->vfo_pitch, b->fs, kNcoStride);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(b->s_compute));
+  }
+  b->dev_bytes = bytes;
+  b->finalized = true;
+  return AERODDC_OK;
+}
+
+int aeroddc_bank_submit_device(aeroddc_bank* b, const void* dev_iq, size_t n_complex, void* ready_event) {
+  if (!b || !dev_iq) return fail(AERODDC_ERR_ARG, "NULL argument");
+  if (!b->finalized) return fail(AERODDC_ERR_STATE, "bank not finalized");
+  if (n_complex != (size_t)b->B)
+    return fail(AERODDC_ERR_ARG, "block of %zu samples, bank was created for %d (vfo.cpp:155,164 block contract)", n_complex, b->B);
+  if (b->blocks_submitted - b->blocks_done >= 2) return fail(AERODDC_ERR_STATE, "two blocks already in flight; call wait()");
+  if ((uintptr_t)dev_iq & 15) return fail(AERODDC_ERR_ARG, "device block must be 16-byte aligned");
+  CU(cudaSetDevice(b->device));
+  if (ready_event) CU(cudaStreamWaitEvent(b->s_compute, (cudaEvent_t)ready_event, 0));
+  return enqueue_block(b, dev_iq);
+}
+
+int aeroddc_bank_submit(aeroddc_bank* b, const void* host_iq, size_t n_complex) {
+  if (!b || !host_iq) return fail(AERODDC_ERR_ARG, "NULL argument");
+  if (!b->finalized) return fail(AERODDC_ERR_STATE, "bank not finalized");
+  if (n_complex != (size_t)b->B)
+    return fail(AERODDC_ERR_ARG, "block of %zu samples, bank was created for %d (vfo.cpp:155,164 block contract)", n_complex, b->B);
+  if (b->blocks_submitted - b->blocks_done >= 2) return fail(AERODDC_ERR_STATE, "two blocks already in flight; call wait()");
+  CU(cudaSetDevice(b->device));
+  const int slot = (int)(b->blocks_submitted & 1);
+  const void* src = host_iq;
+  if (host_iq != b->h_in[0] && host_iq != b->h_in[1]) {   // pageable caller memory: stage through the pinned ring
+    memcpy(b->h_in[slot], host_iq, b->in_bytes);
+    src = b->h_in[slot];
+  }
+  // d_in[slot] was last read by the block submitted two calls ago, which wait() has retired
+  CU(cudaMemcpyAsync(b->d_in[slot], src, b->in_bytes, cudaMemcpyHostToDevice, b->s_copy));
+  CU(cudaEventRecord(b->ev_h2d[slot], b->s_copy));
+  CU(cudaStreamWaitEvent(b->s_compute, b->ev_h2d[slot], 0));
+  return enqueue_block(b, b->d_in[slot]);
+}
+
+int aeroddc_bank_wait(aeroddc_bank* b) {
+  if (!b) return fail(AERODDC_ERR_ARG, "NULL bank");
+  if (b->blocks_done >= b->blocks_submitted) return fail(AERODDC_ERR_STATE, "nothing in flight");
+  CU(cudaSetDevice(b->device));
+  const int slot = (int)(b->blocks_done % 3);
+  CU(cudaEventSynchronize(b->ev_done[slot]));
+  CU(cudaEventElapsedTime(&b->last_kernel_ms, b->ev_k0[slot], b->ev_k1[slot]));
+  CU(cudaEventElapsedTime(&b->last_main_ms, b->ev_m0[slot], b->ev_m1[slot]));
+  b->last_launches = b->launches_per_block;
+  b->cur_out = slot;
+  b->blocks_done++;
+  return AERODDC_OK;
+}
+
+int aeroddc_bank_process(aeroddc_bank* b, const void* host_iq, size_t n_complex) {
+  int rc = aeroddc_bank_submit(b, host_iq, n_complex);
+  if (rc != AERODDC_OK) return rc;
+  while (b->blocks_done < b->blocks_submitted) {
+    rc = aeroddc_bank_wait(b);
+    if (rc != AERODDC_OK) return rc;
+  }
+  return AERODDC_OK;
+}
+
+int aeroddc_bank_host_slot(aeroddc_bank* b, int slot, void** ptr, size_t* bytes) {
+  if (!b || !ptr) return fail(AERODDC_ERR_ARG, "NULL argument");
+  if (!b->finalized) return fail(AERODDC_ERR_STATE, "bank not finalized");
+  if (slot < 0 || slot > 1) return fail(AERODDC_ERR_ARG, "slot must be 0 or 1");
+  *ptr = b->h_in[slot];
+  if (bytes) *bytes = b->in_bytes;
+  return AERODDC_OK;
+}
+
+int aeroddc_bank_output(aeroddc_bank* b, int vfo, const void** payload, size_t* nbytes, uint32_t* rate) {
+  if (!b) return fail(AERODDC_ERR_ARG, "NULL bank");
+  if (vfo < 0 || vfo >= (int)b->vfos.size()) return fail(AERODDC_ERR_ARG, "vfo index %d out of range", vfo);
+  if (b->cur_out < 0) return fail(AERODDC_ERR_STATE, "no completed block yet");
+  const VfoRec& r = b->vfos[vfo];
+  if (payload) *payload = b->h_out[b->cur_out] + r.out_off;
+  if (nbytes) *nbytes = r.out_bytes;
+  if (rate) *rate = (uint32_t)r.plan.out_rate;
+  return AERODDC_OK;
+}
+
+const char* aeroddc_bank_topic(aeroddc_bank* b, int vfo) {
+  if (!b || vfo < 0 || vfo >= (int)b->vfos.size()) return "";
+  return b->vfos[vfo].d.topic;
+}
+
+int aeroddc_bank_stage_d(aeroddc_bank* b, int vfo, float* host_out, size_t cap_complex) {
+  if (!b || !host_out) return fail(AERODDC_ERR_ARG, "NULL argument");
+  if (vfo < 0 || vfo >= (int)b->vfos.size()) return fail(AERODDC_ERR_ARG, "vfo index %d out of range", vfo);
+  if (b->blocks_done < 1 || b->blocks_done != b->blocks_submitted) return fail(AERODDC_ERR_STATE, "needs a completed block and nothing in flight");
+  CU(cudaSetDevice(b->device));
+  const VfoRec& r = b->vfos[vfo];
+  // after the history shift the block occupies [hist_max - n_stage_max + ..]: read it back relative to the end
+  const size_t n = std::min<size_t>(cap_complex, (size_t)r.plan.n_stage);
+  const float2* row = b->d_xd + (size_t)r.slot * b->xd_pitch;
+  // the last n_stage samples of this VFO were at [hist_max, hist_max + n_stage); the shift moved
+  // [nstage_max, nstage_max + hist_max) to the front, so only rows still in place are readable here
+  CU(cudaStreamSynchronize(b->s_compute));
+  CU(cudaMemcpy(host_out, row + b->hist_max, n * sizeof(float2), cudaMemcpyDeviceToHost));
+  return (int)r.plan.n_stage;
+}
+
+int aeroddc_bank_num_vfos(aeroddc_bank* b) { return b ? (int)b->vfos.size() : 0; }
+
+int aeroddc_bank_last_timing(aeroddc_bank* b, float* kernel_ms, int* launches) {
+  if (!b) return fail(AERODDC_ERR_ARG, "NULL bank");
+  if (kernel_ms) *kernel_ms = b->last_kernel_ms;
+  if (launches) *launches = b->last_launches;
+  return AERODDC_OK;
+}
+int aeroddc_bank_last_main_ms(aeroddc_bank* b, float* main_ms) {
+  if (!b) return fail(AERODDC_ERR_ARG, "NULL bank");
+  if (main_ms) *main_ms = b->last_main_ms;
+  return AERODDC_OK;
+}
+int aeroddc_bank_device_bytes(aeroddc_bank* b, size_t* bytes) {
+  if (!b || !bytes) return fail(AERODDC_ERR_ARG, "NULL argument");
+  *bytes = b->dev_bytes;
+  return AERODDC_OK;
+}
+
+void aeroddc_bank_destroy(aeroddc_bank* b) {
+  if (!b) return;
+  free_all(b);
+  delete b;
+}
+
+int aeroddc_measure_fp32_peak(int device, double* tflops, double* sm_clock_mhz) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(AERODDC_ERR_CUDA, "no CUDA device");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+  float* out = nullptr;
+  long long* clk = nullptr;
+  CU(cudaMalloc(&out, sizeof(float) * blocks * threads));
+  CU(cudaMalloc(&clk, sizeof(long long)));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  fp32_peak_kernel<<<blocks, threads>>>(out, 2000, 1.0000001f, 1e-9f, clk);
+  CU(cudaDeviceSynchronize());
+  float best = 1e30f;
+  long long cyc = 0;
+  for (int rep = 0; rep < 3; ++rep) {
+    CU(cudaEventRecord(e0));
+    fp32_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001f, 1e-9f, clk);
+    CU(cudaEventRecord(e1));
+    CU(cudaDeviceSynchronize());
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) { best = ms; CU(cudaMemcpy(&cyc, clk, sizeof cyc, cudaMemcpyDeviceToHost)); }
+  }
+  const double fma_lanes = (double)iters * 64 * 2 * (double)blocks * threads;   // packed: 2 lanes per instruction
+  if (tflops) *tflops = 2.0 * fma_lanes / (best * 1e-3) / 1e12;
+  // one block's clock64 span over the kernel time approximates the SM clock when all blocks are co-resident
+  if (sm_clock_mhz) *sm_clock_mhz = (double)cyc / (best * 1e-3) / 1e6;
+  cudaFree(out); cudaFree(clk); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return AERODDC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+/* aeroddc.h - C ABI of the B200-native multi-VFO digital down-converter bank.
+ *
+ * The reference (airframesio/aero-cli, aero-publish) has no plugin/FFI seam for this path: the
+ * seam is the C++ class `vfo` and the .ini semantics of Publisher::loadSettings. Each entry point
+ * below names the reference interface it stands in for (paths under /root/reference/publish).
+ * The C++ classes in aero-cli_b200/host/ (`vfo`, `Publisher`) keep the reference's method names on
+ * top of this ABI; INTEGRATION.md shows the few lines a maintainer changes in publisher.cpp.
+ *
+ * Conventions: plain pointers and sizes; every function returns AERODDC_OK (0) or a negative
+ * error code and records a message retrievable with aeroddc_last_error(); no exceptions cross the
+ * boundary; a bank handle is NOT thread-safe (the reference drives all VFOs from one worker
+ * thread, publisher.cpp:229-232,301-305). There is no CPU fallback: without a CUDA device every
+ * compute entry point fails with AERODDC_ERR_CUDA.
+ */
+#ifndef AERODDC_H
+#define AERODDC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AERODDC_ABI_VERSION 1
+
+enum {
+  AERODDC_OK = 0,
+  AERODDC_ERR_ARG = -1,    /* bad argument / contract violation (block size, divisibility, ...) */
+  AERODDC_ERR_STATE = -2,  /* call order (add after finalize, process before finalize, ...)     */
+  AERODDC_ERR_CUDA = -3,   /* CUDA runtime error, or no device                                  */
+  AERODDC_ERR_DESIGN = -4, /* filter design rejected the parameters (firfilter.cpp:100-112)     */
+  AERODDC_ERR_NOMEM = -5
+};
+
+/* Raw IQ sample formats of a block (interleaved I,Q). cf32 is what the reference receives from
+ * SoapySDR (publisher.cpp:254,267-268); cu8 and cs16 are the IQ-file-source formats, converted as
+ * (u8 - 127.4f) / 128.0f and s16 / 32768.0f. */
+enum { AERODDC_CU8 = 0, AERODDC_CS16 = 1, AERODDC_CF32 = 2 };
+
+typedef struct aeroddc_bank aeroddc_bank;
+
+/* One VFO, i.e. the arguments of the vfo setters + init (vfo.h:16-40, vfo.cpp:57-139) as
+ * Publisher::loadSettings fills them (publisher.cpp:118-148,159-219). */
+typedef struct aeroddc_vfo_desc {
+  double mixer_freq;   /* vfo::setMixerFreq: Hz, NCO frequency relative to the bank's centre          */
+  int decim_count;     /* vfo::setDecimationCount: number of half-band /2 stages D, 0..8             */
+  int late_decimate;   /* vfo::init(.., lateDecimate): 0, or 5/6 for the final FIR decimation        */
+  int filter_bw;       /* vfo::setFilterBandwidth: Hz, 0 = no fir_usb                                */
+  float gain;          /* vfo::setGain (the ini value / 100, publisher.cpp:213)                      */
+  int demod_usb;       /* vfo::setDemodUSB: 1 = USB-demodulated int16 audio, 0 = compressed IQ       */
+  int compress_style;  /* vfo::setCompressonStyle: 1 = nibble-packed, 0 = int8 I,Q (demod_usb == 0)  */
+  int scale_comp;      /* vfo::setScaleComp (>0)                                                     */
+  char topic[64];      /* vfo::setZmqTopic; the wire carries its first 5 bytes (zmqpublisher.cpp:69) */
+} aeroddc_vfo_desc;
+
+/* Create an empty bank for blocks of exactly `block_len` complex samples at rate `sample_rate`
+ * in format `in_format`, on CUDA device `device`.
+ * Replaces: the per-VFO setFs()/init(samplesPerBuffer) pair (vfo.cpp:57-139, 141-142) and the
+ * buflen arithmetic of Publisher::loadSettings (publisher.cpp:93-100). */
+int aeroddc_bank_create(aeroddc_bank **out, int sample_rate, int block_len, int in_format, int device);
+
+/* Append a VFO; returns its index (>= 0) or a negative error code.
+ * Replaces: `new vfo()` + setters in publisher.cpp:121-147 and :159-217. */
+int aeroddc_bank_add_vfo(aeroddc_bank *bank, const aeroddc_vfo_desc *desc);
+
+/* Design all filters on the host (firfilter::low_pass, FIRHilbert taps, oscillator rotation;
+ * firfilter.cpp:46-99, dsp.cpp:181-215, oscillator.cpp:8-10), upload them, and run the NCO
+ * checkpoint kernel (Oscillator::Oscillator, oscillator.cpp:12-27). Replaces: vfo::init. */
+int aeroddc_bank_finalize(aeroddc_bank *bank);
+
+/* Process one block given in HOST memory: host->device copy, all kernels, device->host copy of
+ * every VFO's payload, then returns (synchronous). n_complex must equal block_len (the reference's
+ * block contract, vfo.cpp:155,164).
+ * Replaces: Publisher::demodData -> vfo::process for every VFO (publisher.cpp:285-306,
+ * vfo.cpp:154-186), up to but excluding ZmqPublisher::publish. */
+int aeroddc_bank_process(aeroddc_bank *bank, const void *host_iq, size_t n_complex);
+
+/* Pipelined form of the same: submit() enqueues H2D + kernels + D2H for one block and returns;
+ * wait() blocks until the OLDEST submitted block's payloads are in host memory and makes them
+ * the ones aeroddc_bank_output() returns. At most two blocks may be in flight. host_iq must stay
+ * valid until the matching wait() unless it lies in the bank's own pinned ring (next call). */
+int aeroddc_bank_submit(aeroddc_bank *bank, const void *host_iq, size_t n_complex);
+int aeroddc_bank_wait(aeroddc_bank *bank);
+
+/* Pinned host staging ring ("pinned host ring plus async H2D", replaces the malloc'ed samplesBuf
+ * of Publisher::readerThread, publisher.cpp:238,267-268): slot 0/1, each block_len samples. A
+ * source that fills these directly avoids one host copy. */
+int aeroddc_bank_host_slot(aeroddc_bank *bank, int slot, void **ptr, size_t *bytes);
+
+/* Same chain on a block that already lies in DEVICE memory (e.g. the destination of an NCCL
+ * broadcast): enqueues the kernels and the payload D2H on the bank's stream after `ready_event`
+ * (a cudaEvent_t, may be NULL) and returns. Finish with aeroddc_bank_wait(). */
+int aeroddc_bank_submit_device(aeroddc_bank *bank, const void *dev_iq, size_t n_complex, void *ready_event);
+
+/* Payload of VFO `vfo` for the most recently completed block: pointer into pinned host memory
+ * (valid until the next wait()/process()), its length in bytes and the output sample rate.
+ * Replaces: transmit_usb / transmit_iq and outputRate as handed to ZmqPublisher::publish
+ * (vfo.cpp:289-313, zmqpublisher.cpp:61-73): frame 3 and frame 2 of the ZeroMQ message. */
+int aeroddc_bank_output(aeroddc_bank *bank, int vfo, const void **payload, size_t *nbytes, uint32_t *rate);
+
+/* Topic string of a VFO (frame 1 is its first 5 bytes). */
+const char *aeroddc_bank_topic(aeroddc_bank *bank, int vfo);
+
+/* Copy the stage-D complex stream (vfo::decimate[decimateCount], vfo.h:39) of the most recently
+ * completed block to host memory as interleaved float I,Q; returns the number of complex samples
+ * or a negative error. Test/debug hook for stage-wise parity. */
+int aeroddc_bank_stage_d(aeroddc_bank *bank, int vfo, float *host_out, size_t cap_complex);
+
+int aeroddc_bank_num_vfos(aeroddc_bank *bank);
+
+/* Device time, in milliseconds, spent by the kernels of the most recently completed block
+ * (CUDA events on the bank's compute stream) and the number of kernels launched for it. */
+int aeroddc_bank_last_timing(aeroddc_bank *bank, float *kernel_ms, int *launches);
+
+/* Device time of the dominant kernel (the fused unpack + mix + half-band cascade) alone. */
+int aeroddc_bank_last_main_ms(aeroddc_bank *bank, float *main_ms);
+
+/* Resource use after finalize: bytes of HBM held by the bank. */
+int aeroddc_bank_device_bytes(aeroddc_bank *bank, size_t *bytes);
+
+void aeroddc_bank_destroy(aeroddc_bank *bank);
+
+/* Last error message of this thread ("" if none). */
+const char *aeroddc_last_error(void);
+
+/* Measure the FP32 FFMA issue peak of `device` with a register-only microbenchmark (the roofline
+ * denominator SURVEY.md section 8d asks to measure in the same run): TFLOP/s counting FMA = 2. */
+int aeroddc_measure_fp32_peak(int device, double *tflops, double *sm_clock_mhz);
+
+int aeroddc_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AERODDC_H */
