@@ -42,6 +42,7 @@ ABI_SYMBOLS = [
     "aeroddc_bank_output", "aeroddc_bank_topic", "aeroddc_bank_stage_d", "aeroddc_bank_num_vfos",
     "aeroddc_bank_last_timing", "aeroddc_bank_last_main_ms", "aeroddc_bank_device_bytes",
     "aeroddc_bank_destroy", "aeroddc_last_error", "aeroddc_measure_fp32_peak", "aeroddc_abi_version",
+    "aeroddc_design_lowpass", "aeroddc_design_hilbert", "aeroddc_design_rotation",
 ]
 
 _lib = None
@@ -76,6 +77,10 @@ def lib():
         L.aeroddc_bank_destroy.restype = None
         L.aeroddc_last_error.restype = ctypes.c_char_p
         L.aeroddc_measure_fp32_peak.argtypes = [ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        cd, fp = ctypes.c_double, ctypes.POINTER(ctypes.c_float)
+        L.aeroddc_design_lowpass.argtypes = [cd, cd, cd, cd, vp, ci]
+        L.aeroddc_design_hilbert.argtypes = [ci, ci, vp, ci]
+        L.aeroddc_design_rotation.argtypes = [cd, cd, fp, fp]
         _lib = L
     return _lib
 
@@ -84,6 +89,26 @@ def _check(rc):
     if rc < 0:
         raise AeroDdcError("aeroddc error %d: %s" % (rc, lib().aeroddc_last_error().decode()))
     return rc
+
+
+def design_lowpass(gain, fs, cutoff, transition):
+    """float32 taps of the Hamming low-pass the bank would upload (host code, no GPU needed)."""
+    n = _check(lib().aeroddc_design_lowpass(gain, fs, cutoff, transition, None, 0))
+    out = np.empty(n, np.float32)
+    _check(lib().aeroddc_design_lowpass(gain, fs, cutoff, transition, out.ctypes.data, n))
+    return out
+
+
+def design_hilbert(length, fs_param):
+    out = np.empty(length, np.float32)
+    _check(lib().aeroddc_design_hilbert(length, fs_param, out.ctypes.data, length))
+    return out
+
+
+def design_rotation(fs, freq):
+    c, s = ctypes.c_float(), ctypes.c_float()
+    _check(lib().aeroddc_design_rotation(fs, freq, ctypes.byref(c), ctypes.byref(s)))
+    return c.value, s.value
 
 
 def measure_fp32_peak(device=0):

@@ -195,6 +195,8 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, f
   unsigned long long pm, pc;
   asm("mov.b64 %0, {%1, %1};" : "=l"(pm) : "f"(m));
   asm("mov.b64 %0, {%1, %1};" : "=l"(pc) : "f"(c));
+  unsigned long long g0, g1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
   const long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -204,6 +206,7 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, f
     }
   }
   const long long t1 = clock64();
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
   float r = 0.0f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -212,7 +215,8 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, f
     r += a + b;
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = r;
-  if (threadIdx.x == 0 && blockIdx.x == 0) clk[0] = t1 - t0;
+  // SM clock in kHz: cycles per nanosecond x 1e6
+  if (threadIdx.x == 0 && blockIdx.x == 0) clk[0] = (long long)((double)(t1 - t0) / (double)(g1 - g0 ? g1 - g0 : 1) * 1e6);
 }
 
 }  // namespace aeroddc

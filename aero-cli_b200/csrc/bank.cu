@@ -185,7 +185,6 @@ int enqueue_block(aeroddc_bank* b, const void* dev_iq) {
     p.Wb = g.Wb;
     p.nco_len = b->fs;
     p.one = 1.0f;
-    p.mone = -1.0f;
     dim3 grid(g.nseg + 1, (g.count + kVfoPerCta - 1) / kVfoPerCta);
     CU(launch_main(b->fmt, std::min(g.D, kFastStages), p, grid, s));
     ++launches;
@@ -216,6 +215,24 @@ int enqueue_block(aeroddc_bank* b, const void* dev_iq) {
 extern "C" {
 
 int aeroddc_abi_version(void) { return AERODDC_ABI_VERSION; }
+
+int aeroddc_design_lowpass(double gain, double fs, double cutoff, double transition, float* taps, int cap) {
+  const std::vector<float> h = design_lowpass(gain, fs, cutoff, transition);
+  if (h.empty()) return fail(AERODDC_ERR_DESIGN, "low_pass rejected fs=%g cutoff=%g transition=%g (firfilter.cpp:100-112)", fs, cutoff, transition);
+  if (taps) std::copy(h.begin(), h.begin() + std::min<size_t>(h.size(), (size_t)std::max(cap, 0)), taps);
+  return (int)h.size();
+}
+int aeroddc_design_hilbert(int len, int fs_param, float* taps, int cap) {
+  if (len < 1) return fail(AERODDC_ERR_ARG, "len must be positive");
+  const std::vector<float> h = design_hilbert(len, fs_param);
+  if (taps) std::copy(h.begin(), h.begin() + std::min<size_t>(h.size(), (size_t)std::max(cap, 0)), taps);
+  return (int)h.size();
+}
+int aeroddc_design_rotation(double fs, double freq, float* cos_out, float* sin_out) {
+  if (!cos_out || !sin_out) return fail(AERODDC_ERR_ARG, "NULL argument");
+  design_rotation(fs, freq, cos_out, sin_out);
+  return AERODDC_OK;
+}
 const char* aeroddc_last_error(void) { return t_err.c_str(); }
 
 int aeroddc_bank_create(aeroddc_bank** out, int sample_rate, int block_len, int in_format, int device) {
@@ -288,7 +305,6 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
     for (int i = 0; i < nv; ++i)
       if (b->vfos[i].d.decim_count == D) { b->vfos[i].slot = col++; g.count++; }
     if (!g.count) continue;
-    if (col & 1) ++col;
     b->groups.push_back(g);
   }
   b->vfo_pitch = (col + 3) & ~3;
@@ -299,7 +315,7 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
     g.W = g.D == 0 ? 0 : ((10 << g.D) + (ilcm(kChunk, 1 << g.D) - 1)) / ilcm(kChunk, 1 << g.D) * ilcm(kChunk, 1 << g.D);
     g.Wb = g.D == 0 ? 0 : (11 << g.D);
     const int nblk_y = (g.count + kVfoPerCta - 1) / kVfoPerCta;
-    const int target = std::max(1, (int)std::floor(2.0 * b->n_sm * waves / nblk_y) - 1);   // -1: the boundary CTA
+    const int target = std::max(1, (int)std::floor((double)kCtasPerSm * b->n_sm * waves / nblk_y) - 1);   // -1: the boundary CTA
     int S = (b->B + target - 1) / target;
     S = std::max(S, std::max(4 * g.W, 4096));
     S = (S + align - 1) / align * align;
@@ -564,8 +580,7 @@ int aeroddc_measure_fp32_peak(int device, double* tflops, double* sm_clock_mhz) 
   }
   const double fma_lanes = (double)iters * 64 * 2 * (double)blocks * threads;   // packed: 2 lanes per instruction
   if (tflops) *tflops = 2.0 * fma_lanes / (best * 1e-3) / 1e12;
-  // one block's clock64 span over the kernel time approximates the SM clock when all blocks are co-resident
-  if (sm_clock_mhz) *sm_clock_mhz = (double)cyc / (best * 1e-3) / 1e6;
+  if (sm_clock_mhz) *sm_clock_mhz = (double)cyc / 1000.0;   // the kernel reports cycles per microsecond x1000
   cudaFree(out); cudaFree(clk); cudaEventDestroy(e0); cudaEventDestroy(e1);
   return AERODDC_OK;
 }

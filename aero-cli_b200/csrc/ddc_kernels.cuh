@@ -21,22 +21,23 @@
 
 namespace aeroddc {
 
-constexpr int kThreads = 128;          // threads per CTA; each thread carries 2 VFOs
-constexpr int kVfoPerCta = 2 * kThreads;
+constexpr int kThreads = 128;          // threads per CTA; each thread carries one VFO
+constexpr int kVfoPerCta = kThreads;
 constexpr int kChunk = 16;             // input samples per unrolled inner step
-constexpr int kTile = 1024;            // input samples per shared-memory tile
+constexpr int kTile = 256;             // input samples per shared-memory tile
 constexpr int kMaxStages = 8;          // hdecimator[8], vfo.h:63
 constexpr int kFastStages = 4;         // half-band stages kept in registers
 constexpr int kStateSlots = 8;         // per stage: 5 even-phase + 3 odd-phase history samples
 constexpr int kNcoStride = 256;        // NCO checkpoint spacing (samples)
+constexpr int kCtasPerSm = 4;          // 16 resident warps per SM at <= 128 registers per thread
 
 enum { FMT_CU8 = 0, FMT_CS16 = 1, FMT_CF32 = 2 };
 
 // ---------------------------------------------------------------------------------------------
-// packed 2 x fp32 arithmetic (lane 0 = VFO A, lane 1 = VFO B), all round-to-nearest, never fused
+// packed 2 x fp32 arithmetic: lane 0 = I (real), lane 1 = Q (imaginary) of ONE VFO.
+// All round-to-nearest, never fused.
 // ---------------------------------------------------------------------------------------------
 struct P2 { unsigned long long v; };
-struct C2 { P2 re, im; };
 
 __device__ __forceinline__ P2 pack2(float a, float b) { P2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ void unpack2(P2 p, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v)); }
@@ -45,14 +46,13 @@ __device__ __forceinline__ P2 mul2(P2 a, P2 b) { P2 d; asm("mul.rn.f32x2 %0, %1,
 __device__ __forceinline__ P2 fma2(P2 a, P2 b, P2 c) { P2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return d; }
 // ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even with -fmad=false (the scalar
 // .rn forms are left alone), which would change the reference's bits. So additions are issued as
-// fma(a, 1.0f, b) and subtractions as fma(b, -1.0f, a), with +-1.0f arriving as kernel parameters
-// (uniform registers) so that ptxas can neither simplify them back to an add nor fuse across them.
-// Each is exactly round(a + b) / round(a - b). FFMA2, FMUL2 and FADD2 share one pipe and rate.
-struct Ones { P2 one, mone; };
+// fma(a, 1.0f, b), with 1.0f arriving as a kernel parameter (a uniform register) so that ptxas can
+// neither simplify it back to an add nor fuse across it. The result is exactly round(a + b).
+// FFMA2, FMUL2 and FADD2 share one pipe and one rate.
+struct Ones { P2 one; };
 __device__ __forceinline__ P2 add2(const Ones& k, P2 a, P2 b) { return fma2(a, k.one, b); }
-__device__ __forceinline__ P2 sub2(const Ones& k, P2 a, P2 b) { return fma2(b, k.mone, a); }
 __device__ __forceinline__ P2 mul2s(P2 a, float s) { return mul2(a, bcast2(s)); }   // FMUL2 R, R.F32x2, R.F32
-__device__ __forceinline__ C2 czero() { C2 z; z.re.v = 0ull; z.im.v = 0ull; return z; }
+__device__ __forceinline__ P2 pzero() { P2 z; z.v = 0ull; return z; }
 
 // half-band taps actually used by the reference (halfbanddecimator.h:84-87, 11-tap set)
 #define HB_P0 0.0060431029837374152f
@@ -60,41 +60,40 @@ __device__ __forceinline__ C2 czero() { C2 z; z.re.v = 0ull; z.im.v = 0ull; retu
 #define HB_P4 0.29332944952052842f
 #define HB_P5 0.5f
 
-// One NCO step for both VFOs: v *= rot; v *= 1.95f - |v|^2   (oscillator.cpp:19-24)
-// complex product as GCC evaluates std::complex<float>: (a*c - b*d, a*d + b*c).
-__device__ __forceinline__ void nco_step(const Ones& k, C2& v, const C2& rot) {
-  P2 ac = mul2(v.re, rot.re), bd = mul2(v.im, rot.im);
-  P2 ad = mul2(v.re, rot.im), bc = mul2(v.im, rot.re);
-  P2 nr = sub2(k, ac, bd), ni = add2(k, ad, bc);
-  P2 s = add2(k, mul2(nr, nr), mul2(ni, ni));
-  P2 nm = sub2(k, bcast2(1.95f), s);
-  v.re = mul2(nr, nm);
-  v.im = mul2(ni, nm);
+// Per-VFO oscillator constants: rotA = (c, d), rotB = (-d, c) with (c, d) = ((float)cos, (float)sin).
+struct Rot { P2 a, b; };
+
+// One NCO step: v *= rot; v *= 1.95f - |v|^2   (oscillator.cpp:19-24), complex product as GCC
+// evaluates std::complex<float>: (a*c - b*d, a*d + b*c). Here (a*c, a*d) + (b*(-d), b*c): negating d
+// is exact, so lane 0 is round(round(a*c) - round(b*d)) as in the reference.
+__device__ __forceinline__ void nco_step(const Ones& k, float& a, float& b, const Rot& rot) {
+  const P2 n = add2(k, mul2s(rot.a, a), mul2s(rot.b, b));
+  float r2, i2;
+  unpack2(mul2(n, n), r2, i2);
+  const float nm = __fsub_rn(1.95f, __fadd_rn(r2, i2));
+  unpack2(mul2s(n, nm), a, b);
 }
 
-// mix: osc * sample  (vfo.cpp:157) -> (a*c - b*d, a*d + b*c), c,d = raw sample shared by both VFOs
-__device__ __forceinline__ C2 mix(const Ones& k, const C2& osc, float c, float d) {
-  C2 r;
-  r.re = sub2(k, mul2s(osc.re, c), mul2s(osc.im, d));
-  r.im = add2(k, mul2s(osc.re, d), mul2s(osc.im, c));
-  return r;
+// mix: osc * sample (vfo.cpp:157) = (a*c - b*d, a*d + b*c), a,b = oscillator, c,d = raw sample:
+// (c, d)*a + (-d, c)*b. ptxas folds the swap and the sign into FMUL2 operand modifiers (.LO_HI.NP).
+__device__ __forceinline__ P2 mix(const Ones& k, float a, float b, const float2& s) {
+  return add2(k, mul2s(pack2(s.x, s.y), a), mul2s(pack2(-s.y, s.x), b));
 }
 
 // Per-stage history in polyphase form: e[k] = x[2(j-5+k)], k<5 (even-phase samples) and
-// o[k] = x[2(j-3+k)+1], k<3 (odd-phase), j = index of the next output.
-struct HbState { C2 e[5]; C2 o[3]; };
+// o[k] = x[2(j-3+k)+1], k<3 (odd-phase), j = index of the next output. Each entry is (I, Q).
+struct HbState { P2 e[5]; P2 o[3]; };
 
-// y[j] = ((p0*(w0+w10) + p2*(w2+w8)) + p4*(w4+w6)) + p5*w5, w[t] = x[2j-10+t]  (dsp.cpp:141-147)
-__device__ __forceinline__ P2 hb_rail(const Ones& k, P2 e0, P2 e1, P2 e2, P2 e3, P2 e4, P2 xe, P2 o0) {
+// y[j] = ((p0*(w0+w10) + p2*(w2+w8)) + p4*(w4+w6)) + p5*w5, w[t] = x[2j-10+t]  (dsp.cpp:141-147),
+// both rails at once
+__device__ __forceinline__ P2 hb_out(const Ones& k, P2 e0, P2 e1, P2 e2, P2 e3, P2 e4, P2 xe, P2 o0) {
   P2 s0 = add2(k, e0, xe), s2 = add2(k, e1, e4), s4 = add2(k, e2, e3);
   P2 m0 = mul2s(s0, HB_P0), m2 = mul2s(s2, HB_P2), m4 = mul2s(s4, HB_P4), m5 = mul2s(o0, HB_P5);
   return add2(k, add2(k, add2(k, m0, m2), m4), m5);
 }
 // consume the pair (x[2j], x[2j+1]) and return output j
-__device__ __forceinline__ C2 hb_pair(const Ones& k, HbState& h, const C2& xe, const C2& xo) {
-  C2 y;
-  y.re = hb_rail(k, h.e[0].re, h.e[1].re, h.e[2].re, h.e[3].re, h.e[4].re, xe.re, h.o[0].re);
-  y.im = hb_rail(k, h.e[0].im, h.e[1].im, h.e[2].im, h.e[3].im, h.e[4].im, xe.im, h.o[0].im);
+__device__ __forceinline__ P2 hb_pair(const Ones& k, HbState& h, P2 xe, P2 xo) {
+  const P2 y = hb_out(k, h.e[0], h.e[1], h.e[2], h.e[3], h.e[4], xe, h.o[0]);
   h.e[0] = h.e[1]; h.e[1] = h.e[2]; h.e[2] = h.e[3]; h.e[3] = h.e[4]; h.e[4] = xe;
   h.o[0] = h.o[1]; h.o[1] = h.o[2]; h.o[2] = xo;
   return y;
@@ -119,7 +118,7 @@ struct MainParams {
   int B, S, W, nseg;         // block length, segment length, warm-up length, segments per block
   int Wb;                    // warm-up of the boundary role: 11*2^D (it needs 11 samples of history per stage)
   int nco_len;               // L = (int)Fs, the oscillator table length
-  float one, mone;           // +1.0f / -1.0f (see add2/sub2)
+  float one;                 // 1.0f (see add2)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -149,6 +148,11 @@ template <int FMT> struct RawBytes { static constexpr int v = FMT == FMT_CU8 ? 2
 // cu8: (u8 - 127.4f) / 128.0f ; cs16: s16 / 32768.0f ; cf32: as is.
 __device__ __forceinline__ float cvt_u8(unsigned v) { return __fdiv_rn(__fsub_rn((float)v, 127.4f), 128.0f); }
 __device__ __forceinline__ float cvt_s16(int v) { return __fdiv_rn((float)v, 32768.0f); }
+template <int FMT> __device__ __forceinline__ float2 load_raw(const void* base, size_t n) {
+  if (FMT == FMT_CU8) { const uchar2 v = reinterpret_cast<const uchar2*>(base)[n]; return make_float2(cvt_u8(v.x), cvt_u8(v.y)); }
+  if (FMT == FMT_CS16) { const short2 v = reinterpret_cast<const short2*>(base)[n]; return make_float2(cvt_s16(v.x), cvt_s16(v.y)); }
+  return reinterpret_cast<const float2*>(base)[n];
+}
 
 // ---------------------------------------------------------------------------------------------
 // The register-resident part of the cascade: kChunk input samples -> kChunk >> NF outputs.
@@ -157,24 +161,21 @@ __device__ __forceinline__ float cvt_s16(int v) { return __fdiv_rn((float)v, 327
 // constructor leaves _vector at the last table entry, oscillator.cpp:12-27).
 // ---------------------------------------------------------------------------------------------
 template <int NF, bool SPECIAL>
-__device__ __forceinline__ void fast_chunk(const Ones& k1, C2& osc, const C2& rot, HbState (&hb)[kFastStages > 0 ? kFastStages : 1],
-                                           const float2* __restrict__ tile, C2 (&out)[kChunk >> NF],
-                                           int& idx, int nco_len, long long n_abs, const C2& qlast) {
-  C2 x0[kChunk];
+__device__ __forceinline__ void fast_chunk(const Ones& k1, float& oa, float& ob, const Rot& rot,
+                                           HbState (&hb)[kFastStages > 0 ? kFastStages : 1],
+                                           const float2* __restrict__ tile, P2 (&out)[kChunk >> NF],
+                                           int& idx, int nco_len, long long n_abs, float qa, float qb) {
+  P2 x0[kChunk];
 #pragma unroll
-  for (int i = 0; i < kChunk; i += 2) {
-    const float4 s = *reinterpret_cast<const float4*>(tile + i);   // two raw samples, broadcast to the warp
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (SPECIAL) {
-        if (idx == nco_len) { idx = 0; osc.re = bcast2(1.0f); osc.im = bcast2(0.0f); }
-      }
-      nco_step(k1, osc, rot);
-      C2 o = osc;
-      if (SPECIAL) { if (n_abs + i + k == 0) o = qlast; }
-      x0[i + k] = k ? mix(k1, o, s.z, s.w) : mix(k1, o, s.x, s.y);
-      if (SPECIAL) idx++;
+  for (int i = 0; i < kChunk; ++i) {
+    const float2 s = tile[i];   // one raw sample (c, d), broadcast to the warp
+    if (SPECIAL) {
+      if (idx == nco_len) { idx = 0; oa = 1.0f; ob = 0.0f; }
     }
+    nco_step(k1, oa, ob, rot);
+    float a = oa, b = ob;
+    if (SPECIAL) { if (n_abs + i == 0) { a = qa; b = qb; } idx++; }
+    x0[i] = mix(k1, a, b, s);
   }
   if (!SPECIAL) idx += kChunk;
   if (NF == 0) {
@@ -182,7 +183,7 @@ __device__ __forceinline__ void fast_chunk(const Ones& k1, C2& osc, const C2& ro
     for (int i = 0; i < kChunk; ++i) out[i >> NF] = x0[i];
     return;
   }
-  C2 x1[kChunk / 2];
+  P2 x1[kChunk / 2];
 #pragma unroll
   for (int j = 0; j < kChunk / 2; ++j) x1[j] = hb_pair(k1, hb[0], x0[2 * j], x0[2 * j + 1]);
   if (NF == 1) {
@@ -190,7 +191,7 @@ __device__ __forceinline__ void fast_chunk(const Ones& k1, C2& osc, const C2& ro
     for (int i = 0; i < kChunk / 2; ++i) out[(i * 2) >> NF] = x1[i];
     return;
   }
-  C2 x2[kChunk / 4];
+  P2 x2[kChunk / 4];
 #pragma unroll
   for (int j = 0; j < kChunk / 4; ++j) x2[j] = hb_pair(k1, hb[NF > 1 ? 1 : 0], x1[2 * j], x1[2 * j + 1]);
   if (NF == 2) {
@@ -198,7 +199,7 @@ __device__ __forceinline__ void fast_chunk(const Ones& k1, C2& osc, const C2& ro
     for (int i = 0; i < kChunk / 4; ++i) out[(i * 4) >> NF] = x2[i];
     return;
   }
-  C2 x3[kChunk / 8];
+  P2 x3[kChunk / 8];
 #pragma unroll
   for (int j = 0; j < kChunk / 8; ++j) x3[j] = hb_pair(k1, hb[NF > 2 ? 2 : 0], x2[2 * j], x2[2 * j + 1]);
   if (NF == 3) {
@@ -210,39 +211,33 @@ __device__ __forceinline__ void fast_chunk(const Ones& k1, C2& osc, const C2& ro
 }
 
 // ---------------------------------------------------------------------------------------------
-// Deep stages (>= kFastStages): history lives in shared memory, [stage][slot][thread].
+// Deep stages (>= kFastStages): history lives in shared memory, [stage][slot][thread], one (I,Q)
+// pair per entry: slots 0..4 = even-phase history (oldest first), 5..7 = odd-phase history.
 // ---------------------------------------------------------------------------------------------
 struct DeepSmem {
-  C2* base;   // this thread's column: element (stage, slot) at base[(stage*kStateSlots + slot) * kThreads]
-  __device__ __forceinline__ C2& at(int stage, int slot) const { return base[(stage * kStateSlots + slot) * kThreads]; }
+  P2* base;   // this thread's column: element (stage, slot) at base[(stage*kStateSlots + slot) * kThreads]
+  __device__ __forceinline__ P2& at(int stage, int slot) const { return base[(stage * kStateSlots + slot) * kThreads]; }
 };
 
 // push one sample into deep stage `ds`; returns true and the output in y when the sample was even-phase
-__device__ __forceinline__ bool deep_push(const Ones& k1, const DeepSmem& sm, int ds, bool odd, const C2& x, C2& y) {
+__device__ __forceinline__ bool deep_push(const Ones& k1, const DeepSmem& sm, int ds, bool odd, P2 x, P2& y) {
   if (odd) {   // store x[2j+1]
     sm.at(ds, 5) = sm.at(ds, 6);
     sm.at(ds, 6) = sm.at(ds, 7);
     sm.at(ds, 7) = x;
     return false;
   }
-  C2 e0 = sm.at(ds, 0), e1 = sm.at(ds, 1), e2 = sm.at(ds, 2), e3 = sm.at(ds, 3), e4 = sm.at(ds, 4), o0 = sm.at(ds, 5);
-  y.re = hb_rail(k1, e0.re, e1.re, e2.re, e3.re, e4.re, x.re, o0.re);
-  y.im = hb_rail(k1, e0.im, e1.im, e2.im, e3.im, e4.im, x.im, o0.im);
+  const P2 e0 = sm.at(ds, 0), e1 = sm.at(ds, 1), e2 = sm.at(ds, 2), e3 = sm.at(ds, 3), e4 = sm.at(ds, 4), o0 = sm.at(ds, 5);
+  y = hb_out(k1, e0, e1, e2, e3, e4, x, o0);
   sm.at(ds, 0) = e1; sm.at(ds, 1) = e2; sm.at(ds, 2) = e3; sm.at(ds, 3) = e4; sm.at(ds, 4) = x;
   return true;
 }
 
-__device__ __forceinline__ C2 load_c2(const float2* p) {   // p -> two consecutive VFOs (16 B aligned)
-  const float4 v = *reinterpret_cast<const float4*>(p);
-  C2 r; r.re = pack2(v.x, v.z); r.im = pack2(v.y, v.w); return r;
-}
-__device__ __forceinline__ void store_c2(float2* p, const C2& c) {
-  float ar, br, ai, bi; unpack2(c.re, ar, br); unpack2(c.im, ai, bi);
-  *reinterpret_cast<float4*>(p) = make_float4(ar, ai, br, bi);
-}
+__device__ __forceinline__ P2 load_p2(const float2* p) { const float2 v = *p; return pack2(v.x, v.y); }
+__device__ __forceinline__ void store_p2(float2* p, P2 c) { float a, b; unpack2(c, a, b); *p = make_float2(a, b); }
 
 // ---------------------------------------------------------------------------------------------
-// Boundary role: recompute, from the last W samples of this block, the history every stage of
+// Boundary role: recompute, from the last Wb samples of this block, the history every stage of
 // every VFO will see at the start of the NEXT block. The reference re-seeds each half-band queue
 // with queue[n-1 .. n+9] instead of the last 11 samples (FIR::FIRQueueBackToFront, dsp.cpp:163-172):
 // history index l<0 of the next block is this block's sample n-1+l, so the newest sample x[n-1]
@@ -250,41 +245,39 @@ __device__ __forceinline__ void store_c2(float2* p, const C2& c) {
 // block's even-phase history is this block's odd samples o[n/2-6 .. n/2-2] and its odd-phase
 // history is this block's even samples e[n/2-3 .. n/2-1].
 // Straightforward per-thread code with local-memory rings; it runs on one extra CTA per VFO group
-// concurrently with the main CTAs, so its speed does not matter.
+// concurrently with the segment CTAs, so its speed does not matter.
 // ---------------------------------------------------------------------------------------------
 template <int FMT>
-__device__ void boundary_role(const MainParams& p, int vfo0, bool active) {
-  C2 eh[kMaxStages][5];
-  C2 oh[kMaxStages][6];
+__device__ void boundary_role(const MainParams& p, int vfo, bool active) {
+  P2 eh[kMaxStages][5];
+  P2 oh[kMaxStages][6];
 #pragma unroll 1
   for (int s = 0; s < kMaxStages; ++s) {
-    for (int k = 0; k < 5; ++k) eh[s][k] = czero();
-    for (int k = 0; k < 6; ++k) oh[s][k] = czero();
+    for (int k = 0; k < 5; ++k) eh[s][k] = pzero();
+    for (int k = 0; k < 6; ++k) oh[s][k] = pzero();
   }
-  Ones k1; k1.one = bcast2(p.one); k1.mone = bcast2(p.mone);
-  C2 rot, osc, qlast;
-  rot = load_c2(p.rot + vfo0);
-  qlast = load_c2(p.qlast + vfo0);
+  Ones k1; k1.one = bcast2(p.one);
+  const float2 r = p.rot[vfo];
+  Rot rot; rot.a = pack2(r.x, r.y); rot.b = pack2(-r.y, r.x);
+  const float2 ql = p.qlast[vfo];
   const int start = p.B - p.Wb;                      // in-block index of the first warm-up sample
   const long long n0 = p.block_abs + start;
   int idx = (int)(n0 % p.nco_len);
+  float oa, ob;
   {
-    const int ck = idx / kNcoStride, r = idx % kNcoStride;
-    osc = load_c2(p.ckpt + (size_t)ck * p.vfo_pitch + vfo0);
-    for (int i = 0; i < r; ++i) nco_step(k1, osc, rot);
+    const int ck = idx / kNcoStride, rem = idx % kNcoStride;
+    const float2 c = p.ckpt[(size_t)ck * p.vfo_pitch + vfo];
+    oa = c.x; ob = c.y;
+    for (int i = 0; i < rem; ++i) nco_step(k1, oa, ob, rot);
   }
   for (int i = 0; i < p.Wb; ++i) {
-    float c, d;
-    const size_t n = (size_t)start + i;
-    if (FMT == FMT_CU8) { const uchar2 v = reinterpret_cast<const uchar2*>(p.iq)[n]; c = cvt_u8(v.x); d = cvt_u8(v.y); }
-    else if (FMT == FMT_CS16) { const short2 v = reinterpret_cast<const short2*>(p.iq)[n]; c = cvt_s16(v.x); d = cvt_s16(v.y); }
-    else { const float2 v = reinterpret_cast<const float2*>(p.iq)[n]; c = v.x; d = v.y; }
-    if (idx == p.nco_len) { idx = 0; osc.re = bcast2(1.0f); osc.im = bcast2(0.0f); }
-    nco_step(k1, osc, rot);
-    C2 o = osc;
-    if (n0 + i == 0) o = qlast;
+    const float2 cd = load_raw<FMT>(p.iq, (size_t)start + i);
+    if (idx == p.nco_len) { idx = 0; oa = 1.0f; ob = 0.0f; }
+    nco_step(k1, oa, ob, rot);
+    float a = oa, b = ob;
+    if (n0 + i == 0) { a = ql.x; b = ql.y; }
     idx++;
-    C2 x = mix(k1, o, c, d);
+    P2 x = mix(k1, a, b, cd);
     int cnt = i;
 #pragma unroll 1
     for (int s = 0; s < p.D; ++s) {
@@ -293,9 +286,7 @@ __device__ void boundary_role(const MainParams& p, int vfo0, bool active) {
         oh[s][5] = x;
         break;
       }
-      C2 y;
-      y.re = hb_rail(k1, eh[s][0].re, eh[s][1].re, eh[s][2].re, eh[s][3].re, eh[s][4].re, x.re, oh[s][3].re);
-      y.im = hb_rail(k1, eh[s][0].im, eh[s][1].im, eh[s][2].im, eh[s][3].im, eh[s][4].im, x.im, oh[s][3].im);
+      const P2 y = hb_out(k1, eh[s][0], eh[s][1], eh[s][2], eh[s][3], eh[s][4], x, oh[s][3]);
       for (int k = 0; k < 4; ++k) eh[s][k] = eh[s][k + 1];
       eh[s][4] = x;
       x = y;
@@ -305,40 +296,42 @@ __device__ void boundary_role(const MainParams& p, int vfo0, bool active) {
   if (active) {
 #pragma unroll 1
     for (int s = 0; s < p.D; ++s) {
-      float2* st = p.state_out + (size_t)s * kStateSlots * p.vfo_pitch + vfo0;
-      for (int k = 0; k < 5; ++k) store_c2(st + (size_t)k * p.vfo_pitch, oh[s][k]);            // o[n/2-6 .. n/2-2]
-      for (int k = 0; k < 3; ++k) store_c2(st + (size_t)(5 + k) * p.vfo_pitch, eh[s][2 + k]);  // e[n/2-3 .. n/2-1]
+      float2* st = p.state_out + (size_t)s * kStateSlots * p.vfo_pitch + vfo;
+      for (int k = 0; k < 5; ++k) store_p2(st + (size_t)k * p.vfo_pitch, oh[s][k]);            // o[n/2-6 .. n/2-2]
+      for (int k = 0; k < 3; ++k) store_p2(st + (size_t)(5 + k) * p.vfo_pitch, eh[s][2 + k]);  // e[n/2-3 .. n/2-1]
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Main kernel. grid = (nseg + 1, vfo groups). blockIdx.x < nseg: segment role; == nseg: boundary.
+// Shared memory: raw tile ring (TMA bulk copies) | converted float tiles (c, d), double-buffered |
+// deep-stage history | mbarriers.
 // ---------------------------------------------------------------------------------------------
 template <int FMT> struct TileSmem {
   static constexpr int kRawStages = 3;
   static constexpr int kRawBytes = kTile * RawBytes<FMT>::v;
-  static constexpr int kF32Bytes = FMT == FMT_CF32 ? 0 : 2 * kTile * 8;
-  static constexpr int kDeepBytes = (kMaxStages - kFastStages) * kStateSlots * kThreads * 16;
-  static constexpr int kTotal = kRawStages * kRawBytes + kF32Bytes + kDeepBytes + 64;
+  static constexpr int kCvtBytes = 2 * kTile * 8;
+  static constexpr int kDeepBytes = (kMaxStages - kFastStages) * kStateSlots * kThreads * 8;
+  static constexpr int kTotal = kRawStages * kRawBytes + kCvtBytes + kDeepBytes + 64;
 };
 
 template <int NF, int FMT>
-__global__ void __launch_bounds__(kThreads, 2) ddc_main_kernel(const MainParams p) {
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const MainParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   using TS = TileSmem<FMT>;
   unsigned char* raw = smem;
-  float2* f32buf = reinterpret_cast<float2*>(smem + TS::kRawStages * TS::kRawBytes);
-  C2* deep = reinterpret_cast<C2*>(smem + TS::kRawStages * TS::kRawBytes + TS::kF32Bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TS::kRawStages * TS::kRawBytes + TS::kF32Bytes + TS::kDeepBytes);
+  float2* cvt = reinterpret_cast<float2*>(smem + TS::kRawStages * TS::kRawBytes);
+  P2* deep = reinterpret_cast<P2*>(smem + TS::kRawStages * TS::kRawBytes + TS::kCvtBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TS::kRawStages * TS::kRawBytes + TS::kCvtBytes + TS::kDeepBytes);
 
   const int tid = threadIdx.x;
-  const int slot = blockIdx.y * kVfoPerCta + 2 * tid;     // first of this thread's two VFOs within the slice
+  const int slot = blockIdx.y * kVfoPerCta + tid;       // this thread's VFO within the slice
   const bool active = slot < p.vfo_count;
-  const int vfo0 = p.vfo_base + (active ? slot : 0);      // inactive threads shadow VFO pair 0, never store
+  const int vfo = p.vfo_base + (active ? slot : 0);     // inactive threads shadow VFO 0 of the slice, never store
 
   if ((int)blockIdx.x == p.nseg) {
-    if (p.D > 0) boundary_role<FMT>(p, vfo0, active);
+    if (p.D > 0) boundary_role<FMT>(p, vfo, active);
     return;
   }
 
@@ -363,57 +356,54 @@ __global__ void __launch_bounds__(kThreads, 2) ddc_main_kernel(const MainParams 
     mbar_expect_tx(bar, bytes);
     tma_bulk_g2s(raw + (t % TS::kRawStages) * TS::kRawBytes, gsrc + (size_t)t * TS::kRawBytes, bytes, bar);
   };
-  // cf32 tiles are consumed in place, so a slot is refilled one iteration after its tile was used;
-  // cu8/cs16 tiles are converted out of the slot first, so it can be refilled at once
-  constexpr int kPrefetch = FMT == FMT_CF32 ? TS::kRawStages - 1 : TS::kRawStages;
   if (tid == 0) {
-    for (int t = 0; t < kPrefetch && t < ntiles; ++t) issue(t);
+    for (int t = 0; t < TS::kRawStages && t < ntiles; ++t) issue(t);
   }
 
   // ---- per-thread state ----
-  Ones k1; k1.one = bcast2(p.one); k1.mone = bcast2(p.mone);
-  C2 rot = load_c2(p.rot + vfo0);
-  const C2 qlast = load_c2(p.qlast + vfo0);
+  Ones k1; k1.one = bcast2(p.one);
+  const float2 r = p.rot[vfo];
+  Rot rot; rot.a = pack2(r.x, r.y); rot.b = pack2(-r.y, r.x);
+  const float2 ql = p.qlast[vfo];
   HbState hb[kFastStages > 0 ? kFastStages : 1];
   DeepSmem dsm; dsm.base = deep + tid;
   const int ndeep = p.D > NF ? p.D - NF : 0;
   if (seg == 0) {
 #pragma unroll
     for (int s = 0; s < NF; ++s) {
-      const float2* st = p.state_in + (size_t)s * kStateSlots * p.vfo_pitch + vfo0;
+      const float2* st = p.state_in + (size_t)s * kStateSlots * p.vfo_pitch + vfo;
 #pragma unroll
-      for (int k = 0; k < 5; ++k) hb[s].e[k] = load_c2(st + (size_t)k * p.vfo_pitch);
+      for (int k = 0; k < 5; ++k) hb[s].e[k] = load_p2(st + (size_t)k * p.vfo_pitch);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) hb[s].o[k] = load_c2(st + (size_t)(5 + k) * p.vfo_pitch);
+      for (int k = 0; k < 3; ++k) hb[s].o[k] = load_p2(st + (size_t)(5 + k) * p.vfo_pitch);
     }
     for (int s = 0; s < ndeep; ++s) {
-      const float2* st = p.state_in + (size_t)(NF + s) * kStateSlots * p.vfo_pitch + vfo0;
-      for (int k = 0; k < kStateSlots; ++k) dsm.at(s, k) = load_c2(st + (size_t)k * p.vfo_pitch);
+      const float2* st = p.state_in + (size_t)(NF + s) * kStateSlots * p.vfo_pitch + vfo;
+      for (int k = 0; k < kStateSlots; ++k) dsm.at(s, k) = load_p2(st + (size_t)k * p.vfo_pitch);
     }
   } else {
 #pragma unroll
     for (int s = 0; s < NF; ++s) {
 #pragma unroll
-      for (int k = 0; k < 5; ++k) hb[s].e[k] = czero();
+      for (int k = 0; k < 5; ++k) hb[s].e[k] = pzero();
 #pragma unroll
-      for (int k = 0; k < 3; ++k) hb[s].o[k] = czero();
+      for (int k = 0; k < 3; ++k) hb[s].o[k] = pzero();
     }
     for (int s = 0; s < ndeep; ++s)
-      for (int k = 0; k < kStateSlots; ++k) dsm.at(s, k) = czero();
+      for (int k = 0; k < kStateSlots; ++k) dsm.at(s, k) = pzero();
   }
   long long n_abs = p.block_abs + first;
   int idx = (int)(n_abs % p.nco_len);
-  C2 osc;
+  float oa, ob;
   {
-    const int ck = idx / kNcoStride, r = idx % kNcoStride;
-    osc = load_c2(p.ckpt + (size_t)ck * p.vfo_pitch + vfo0);
-    for (int i = 0; i < r; ++i) nco_step(k1, osc, rot);
+    const int ck = idx / kNcoStride, rem = idx % kNcoStride;
+    const float2 c = p.ckpt[(size_t)ck * p.vfo_pitch + vfo];
+    oa = c.x; ob = c.y;
+    for (int i = 0; i < rem; ++i) nco_step(k1, oa, ob, rot);
   }
 
   // stage-D output cursor: outputs before the segment start (warm-up) are discarded
-  float2* xdA = p.xd + (size_t)vfo0 * p.xd_pitch + p.xd_hist;
-  float2* xdB = xdA + p.xd_pitch;
-  const bool activeB = slot + 1 < p.vfo_count;
+  float2* xd = p.xd + (size_t)vfo * p.xd_pitch + p.xd_hist;
   const int out_first = seg_start >> p.D;                 // first stage-D index this segment owns
   int out_pos = first >> p.D;                             // stage-D index of the next output produced
   unsigned chunk_ctr = 0;                                 // chunks since `first` (first is 2^D aligned)
@@ -421,61 +411,45 @@ __global__ void __launch_bounds__(kThreads, 2) ddc_main_kernel(const MainParams 
   for (int t = 0; t < ntiles; ++t) {
     const int n = min(kTile, total - t * kTile);
     mbar_wait(&bars[t % TS::kRawStages], (t / TS::kRawStages) & 1);
-    const float2* tile;
-    if (FMT == FMT_CF32) {
-      tile = reinterpret_cast<const float2*>(raw + (t % TS::kRawStages) * TS::kRawBytes);
-      // all threads are done with tile t-1 before its slot is refilled with tile t+2
-      __syncthreads();
-      if (tid == 0 && t + TS::kRawStages - 1 < ntiles) issue(t + TS::kRawStages - 1);
-    } else {
-      float2* dst = f32buf + (t & 1) * kTile;
+    // unpack once per CTA: raw -> float (c, d), shared by every VFO of the CTA
+    float2* dst = cvt + (t & 1) * kTile;
+    {
       const unsigned char* src = raw + (t % TS::kRawStages) * TS::kRawBytes;
-      for (int i = tid; i < n; i += kThreads) {
-        if (FMT == FMT_CU8) { const uchar2 v = reinterpret_cast<const uchar2*>(src)[i]; dst[i] = make_float2(cvt_u8(v.x), cvt_u8(v.y)); }
-        else { const short2 v = reinterpret_cast<const short2*>(src)[i]; dst[i] = make_float2(cvt_s16(v.x), cvt_s16(v.y)); }
-      }
-      __syncthreads();   // conversions visible; everyone has finished computing on f32buf[(t-1)&1]
-      if (tid == 0 && t + TS::kRawStages < ntiles) issue(t + TS::kRawStages);
-      tile = dst;
+      for (int i = tid; i < n; i += kThreads) dst[i] = load_raw<FMT>(src, i);
     }
+    __syncthreads();   // converted tile visible; everyone has finished computing on cvt[(t-1)&1]
+    if (tid == 0 && t + TS::kRawStages < ntiles) issue(t + TS::kRawStages);   // raw slot is free again
+    const float2* tile = dst;
 
 #pragma unroll 1
     for (int c = 0; c < n; c += kChunk) {
-      C2 out[kChunk >> NF];
+      P2 out[kChunk >> NF];
       const bool special = (idx + kChunk > p.nco_len) || (n_abs == 0);
-      if (special) fast_chunk<NF, true>(k1, osc, rot, hb, tile + c, out, idx, p.nco_len, n_abs, qlast);
-      else         fast_chunk<NF, false>(k1, osc, rot, hb, tile + c, out, idx, p.nco_len, n_abs, qlast);
+      if (special) fast_chunk<NF, true>(k1, oa, ob, rot, hb, tile + c, out, idx, p.nco_len, n_abs, ql.x, ql.y);
+      else         fast_chunk<NF, false>(k1, oa, ob, rot, hb, tile + c, out, idx, p.nco_len, n_abs, ql.x, ql.y);
       n_abs += kChunk;
       if (NF < kFastStages) {
         // D == NF < 4: every fast output is a stage-D sample
 #pragma unroll
         for (int i = 0; i < (kChunk >> NF); ++i) {
-          if (out_pos >= out_first) {
-            float ar, br, ai, bi; unpack2(out[i].re, ar, br); unpack2(out[i].im, ai, bi);
-            if (active) xdA[out_pos] = make_float2(ar, ai);
-            if (activeB) xdB[out_pos] = make_float2(br, bi);
-          }
+          if (out_pos >= out_first && active) store_p2(xd + out_pos, out[i]);
           out_pos++;
         }
       } else {
         // one stage-4 sample per chunk ripples through the deep stages
-        C2 x = out[0];
+        P2 x = out[0];
         unsigned cc = chunk_ctr;
         int s = 0;
         bool produced = true;
 #pragma unroll 1
         for (; s < ndeep; ++s) {
-          C2 y;
+          P2 y;
           if (!deep_push(k1, dsm, s, cc & 1u, x, y)) { produced = false; break; }
           x = y;
           cc >>= 1;
         }
         if (produced) {
-          if (out_pos >= out_first) {
-            float ar, br, ai, bi; unpack2(x.re, ar, br); unpack2(x.im, ai, bi);
-            if (active) xdA[out_pos] = make_float2(ar, ai);
-            if (activeB) xdB[out_pos] = make_float2(br, bi);
-          }
+          if (out_pos >= out_first && active) store_p2(xd + out_pos, x);
           out_pos++;
         }
         chunk_ctr++;

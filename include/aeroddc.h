@@ -128,6 +128,15 @@ const char *aeroddc_last_error(void);
  * denominator SURVEY.md section 8d asks to measure in the same run): TFLOP/s counting FMA = 2. */
 int aeroddc_measure_fp32_peak(int device, double *tflops, double *sm_clock_mhz);
 
+/* Host-side coefficient designers, exposed so that callers and tests can inspect exactly the taps
+ * the bank uploads. Pure CPU code (no device needed), bit-identical to firfilter::low_pass with the
+ * Hamming window (firfilter.cpp:46-99,186-193), FIRHilbert::FIRHilbert (dsp.cpp:181-215) and the
+ * oscillator rotation (oscillator.cpp:8-10). The tap functions return the tap count (writing at
+ * most `cap` taps) or AERODDC_ERR_DESIGN when the reference would throw (firfilter.cpp:100-112). */
+int aeroddc_design_lowpass(double gain, double fs, double cutoff, double transition, float *taps, int cap);
+int aeroddc_design_hilbert(int len, int fs_param, float *taps, int cap);
+int aeroddc_design_rotation(double fs, double freq, float *cos_out, float *sin_out);
+
 int aeroddc_abi_version(void);
 
 #ifdef __cplusplus
