@@ -1,0 +1,94 @@
+"""CPU suite, part 2: the C-ABI library loads, exports every symbol include/aeroddc.h declares,
+refuses to compute without a CUDA device (no CPU fallback), and its host-side designers agree
+bit for bit with the oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import aeroddc
+from oracle_bind import oracle_lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "aeroddc.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(aeroddc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = aeroddc.lib()
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), "libaeroddc.so does not export %s" % s
+    assert sorted(aeroddc.ABI_SYMBOLS) == syms, "binding list out of date with include/aeroddc.h"
+    assert lib.aeroddc_abi_version() == 1
+
+
+def _has_gpu():
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device behaviour")
+def test_no_cpu_fallback_without_device():
+    with pytest.raises(aeroddc.AeroDdcError) as e:
+        aeroddc.Bank(288000, 57600, aeroddc.CF32, 0)
+    assert "no CUDA device" in str(e.value) or "fallback" in str(e.value)
+
+
+def test_argument_errors_are_reported_before_any_device_use():
+    lib = aeroddc.lib()
+    h = ctypes.c_void_p()
+    assert lib.aeroddc_bank_create(ctypes.byref(h), 0, 100, 2, 0) == -1          # bad rate
+    assert lib.aeroddc_bank_create(ctypes.byref(h), 288000, 288016, 2, 0) == -1  # block longer than Fs (dsp.cpp:43)
+    assert lib.aeroddc_bank_create(ctypes.byref(h), 288000, 57600, 7, 0) == -1   # unknown format
+    assert lib.aeroddc_bank_create(ctypes.byref(h), 288000, 57601, 2, 0) == -1   # not a multiple of 16
+    assert b"multiple" in lib.aeroddc_last_error()
+    assert lib.aeroddc_bank_process(None, None, 0) == -1
+    assert lib.aeroddc_bank_wait(None) == -1
+
+
+@pytest.mark.parametrize("args", [(2, 240000, 24000, 12000.0), (2, 288000, 24000, 9600.0), (2, 48000, 12000, 3000.0),
+                                  (2, 48000, 6000, 1500.0), (2, 48000, 3000, 750.0), (2, 48000, 1500, 375.0), (2, 24000, 3000, 750.0)])
+def test_lowpass_design_matches_oracle(args):
+    got = aeroddc.design_lowpass(*args)
+    buf = np.zeros(8192, np.float32)
+    n = oracle_lib().ddc_lowpass_taps(*args, buf.ctypes.data, 8192)
+    assert n == got.size
+    assert np.array_equal(got.view(np.uint32), buf[:n].view(np.uint32))
+    assert abs(float(got.astype(np.float64).sum()) - 2.0) < 1e-5          # DC gain 2 (vfo.cpp:71-79)
+    assert got.size % 2 == 1
+
+
+def test_lowpass_design_rejects_like_the_reference():
+    lib = aeroddc.lib()
+    assert lib.aeroddc_design_lowpass(2.0, 48000.0, 30000.0, 100.0, None, 0) == -4   # cutoff above fs/2 (firfilter.cpp:100-112)
+    assert lib.aeroddc_design_lowpass(2.0, 48000.0, 3000.0, 0.0, None, 0) == -4      # zero transition width
+
+
+@pytest.mark.parametrize("fs", [12000, 2400, 9600, 15000, 90])
+def test_hilbert_design_matches_oracle(fs):
+    got = aeroddc.design_hilbert(125, fs)
+    want = np.zeros(125, np.float32)
+    oracle_lib().ddc_hilbert_taps(125, fs, want.ctypes.data)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert got[62] == 0.0 and abs(float((got.astype(np.float64) ** 2).sum()) - 1.0) < 1e-6
+
+
+def test_rotation_matches_oracle():
+    O = oracle_lib()
+    O.ddc_nco_rotation.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
+    for fs, f in [(61440000.0, 1234567.0), (288000.0, -34567.0), (1536000.0, 0.0), (2400000.0, 1199999.0)]:
+        c, s = ctypes.c_float(), ctypes.c_float()
+        O.ddc_nco_rotation(fs, f, ctypes.byref(c), ctypes.byref(s))
+        assert aeroddc.design_rotation(fs, f) == (c.value, s.value)

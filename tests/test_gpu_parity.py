@@ -1,0 +1,213 @@
+"""GPU suite (-m gpu): the CUDA bank, called through the C ABI (libaeroddc.so), against
+  * tests/golden/golden.json (outputs of the unmodified reference), byte for byte,
+  * the oracle on seeded multi-VFO banks, all input formats, streaming across block boundaries and
+    NCO table wraps,
+  * size-independent properties at the benchmark's full size (61.44 MS/s, D=8, late /5).
+Tolerance stated by BASELINE.json: max |err| <= 1e-4 of full scale and error SNR >= 80 dB; the
+tests assert the stricter byte identity and also report the tolerance metric."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from case_util import ALL_CASES, case_fmt, check_against_golden, float_block, parity_metrics, raw_block
+from oracle_bind import FMT_CF32, FMT_CS16, FMT_CU8, Oracle, synth_anchor, synth_raw, unpack
+
+pytestmark = pytest.mark.gpu
+
+
+def _aeroddc():
+    import aeroddc
+
+    return aeroddc
+
+
+def make_bank(fs, blk, fmt, vfos):
+    """vfos: list of dicts with mixer, D, L, bw, gain, usb, cstyle, sc."""
+    a = _aeroddc()
+    bank = a.Bank(fs, blk, fmt, 0)
+    for i, v in enumerate(vfos):
+        bank.add_vfo(v["mixer"], v["D"], v.get("L", 0), v.get("bw", 0), v.get("gain", 0.5), v.get("usb", 1),
+                     v.get("cstyle", 1), v.get("sc", 1), "T%04d" % i)
+    bank.finalize()
+    return bank
+
+
+def make_oracles(fs, blk, vfos):
+    return [Oracle(fs, blk, v["D"], v.get("L", 0), v["mixer"], v.get("gain", 0.5), v.get("bw", 0), v.get("usb", 1),
+                   v.get("cstyle", 1), v.get("sc", 1)) for v in vfos]
+
+
+@pytest.mark.parametrize("d", ALL_CASES, ids=[c["name"] for c in ALL_CASES])
+def test_golden_cases_byte_identical(d):
+    bank = make_bank(d["Fs"], d["B"], case_fmt(d), [dict(mixer=d["mixer"], D=d["D"], L=d["L"], bw=d["filter_bw"], gain=d["gain"],
+                                                          usb=d["demod_usb"], cstyle=d["cstyle"], sc=d["scalecomp"])])
+    blocks, rate = [], 0
+    for b in range(d["blocks"]):
+        bank.process(raw_block(d, b))
+        payload, rate = bank.output(0)
+        blocks.append(payload)
+    stage = bank.stage_d(0, d["B"] >> d["D"])
+    check_against_golden(d["name"], blocks, stage, rate)
+    bank.close()
+
+
+def _mixed_bank(fs, n, rng, d_choices, late=0, bw_choices=(0,)):
+    vfos = []
+    for i in range(n):
+        vfos.append(dict(mixer=float(rng.integers(int(-0.45 * fs), int(0.45 * fs))), D=int(d_choices[i % len(d_choices)]), L=late,
+                         bw=int(bw_choices[i % len(bw_choices)]), gain=float(rng.uniform(0.05, 0.5))))
+    return vfos
+
+
+def test_ini_style_bank_mixed_decimation_vs_oracle():
+    """Config B shape: 30 VFOs at 1.536 MS/s, 20 x D=7 (600 bps), 8 x D=6 (1200), 2 x D=5 (10500)."""
+    fs, blk = 1536000, 384000
+    rng = np.random.default_rng(7)
+    vfos = _mixed_bank(fs, 30, rng, [7] * 20 + [6] * 8 + [5] * 2)
+    for v in vfos:
+        v["gain"] = float(rng.uniform(5, 10)) / 100
+    bank = make_bank(fs, blk, FMT_CF32, vfos)
+    oracles = make_oracles(fs, blk, vfos)
+    worst = (0.0, float("inf"))
+    for b in range(5):   # 5 blocks: four boundaries and the NCO table wrap at sample Fs
+        x = synth_raw(FMT_CF32, b * blk, blk, seed=21, amp=0.7)
+        bank.process(x)
+        for i, o in enumerate(oracles):
+            want = o.process(x)
+            got, rate = bank.output(i)
+            assert rate == o.out_rate
+            m = parity_metrics(np.frombuffer(got, np.int16), np.frombuffer(want, np.int16))
+            worst = (max(worst[0], m[0]), min(worst[1], m[1]))
+            assert got == want, "VFO %d block %d: max|err|/FS %.2e, SNR %.1f dB" % (i, b, m[0], m[1])
+    assert worst[0] <= 1e-4 and worst[1] >= 80.0
+    bank.close()
+
+
+@pytest.mark.parametrize("fmt", [FMT_CU8, FMT_CS16, FMT_CF32])
+def test_all_input_formats_vs_oracle(fmt):
+    fs, blk = 2400000, 480000
+    rng = np.random.default_rng(3)
+    vfos = _mixed_bank(fs, 9, rng, [5, 4, 3, 2, 1, 0, 5, 5, 5])
+    vfos[6]["bw"] = 6000
+    vfos[7].update(usb=0, cstyle=1, sc=2)
+    vfos[8].update(usb=0, cstyle=0)
+    bank = make_bank(fs, blk, fmt, vfos)
+    oracles = make_oracles(fs, blk, vfos)
+    for b in range(6):   # B = Fs/5: the table wraps at the start of block 5
+        raw = synth_raw(fmt, b * blk, blk, seed=5, amp=0.8)
+        x = raw if fmt == FMT_CF32 else unpack(fmt, raw)
+        bank.process(raw)
+        for i, o in enumerate(oracles):
+            assert bank.output(i)[0] == o.process(x), "fmt %d VFO %d block %d" % (fmt, i, b)
+    bank.close()
+
+
+def test_pipelined_submit_wait_equals_process():
+    fs, blk = 288000, 57600
+    rng = np.random.default_rng(9)
+    vfos = _mixed_bank(fs, 5, rng, [1, 2, 3, 4, 0], late=0)
+    a = make_bank(fs, blk, FMT_CF32, vfos)
+    b = make_bank(fs, blk, FMT_CF32, vfos)
+    xs = [synth_anchor(k * blk, blk) for k in range(6)]
+    seq = []
+    for x in xs:
+        a.process(x)
+        seq.append([a.output(i)[0] for i in range(5)])
+    got = []
+    b.submit(xs[0])
+    for k in range(1, 6):
+        b.submit(xs[k])
+        b.wait()
+        got.append([b.output(i)[0] for i in range(5)])
+    b.wait()
+    got.append([b.output(i)[0] for i in range(5)])
+    assert got == seq
+    a.close()
+    b.close()
+
+
+def test_block_contract_and_state_errors():
+    a = _aeroddc()
+    bank = a.Bank(288000, 57600, a.CF32, 0)
+    with pytest.raises(a.AeroDdcError):
+        bank.finalize()                     # no VFOs
+    with pytest.raises(a.AeroDdcError):
+        bank.add_vfo(0.0, 9)                # more than 8 half-band stages (vfo.h:63)
+    with pytest.raises(a.AeroDdcError):
+        bank.add_vfo(0.0, 4, 7)             # 3600 stage-D samples not divisible by 7
+    with pytest.raises(a.AeroDdcError):
+        bank.add_vfo(1000.0, 2, 0, 80000)   # fir_usb cutoff above fs/2: the reference's low_pass throws (firfilter.cpp:100-112)
+    bank.add_vfo(1000.0, 2)
+    with pytest.raises(a.AeroDdcError):
+        bank.process(np.zeros(2 * 57600, np.float32))   # not finalized
+    bank.finalize()
+    with pytest.raises(a.AeroDdcError):
+        bank.add_vfo(2000.0, 2)             # after finalize
+    with pytest.raises(a.AeroDdcError):
+        bank.process(np.zeros(2 * 1000, np.float32))    # wrong block length (vfo.cpp:155,164 block contract)
+    with pytest.raises(a.AeroDdcError):
+        bank.output(0)                      # nothing processed yet
+    bank.process(np.zeros(2 * 57600, np.float32))
+    assert bank.output(0)[0] == b"\x00" * (2 * 14400)   # silence in, silence out
+    bank.close()
+
+
+def test_vfo_independence_and_segmentation_invariance(monkeypatch):
+    """A VFO's bytes do not depend on which other VFOs share the bank, on its column, or on how the
+    block is cut into time segments (warm-up + boundary-state logic)."""
+    fs, blk = 1536000, 384000
+    rng = np.random.default_rng(17)
+    vfos = _mixed_bank(fs, 140, rng, [5, 6, 7, 5])   # > 128: two VFO groups per segment
+    xs = [synth_raw(FMT_CF32, k * blk, blk, seed=33, amp=0.7) for k in range(3)]
+    big = make_bank(fs, blk, FMT_CF32, vfos)
+    ref = {}
+    for x in xs:
+        big.process(x)
+        for i in (0, 1, 63, 127, 128, 139):
+            ref.setdefault(i, []).append(big.output(i)[0])
+    big.close()
+    for waves in ("0.25", "3"):
+        monkeypatch.setenv("AERODDC_WAVES", waves)
+        small = make_bank(fs, blk, FMT_CF32, [vfos[i] for i in (139, 0, 128)])
+        for k, x in enumerate(xs):
+            small.process(x)
+            assert small.output(0)[0] == ref[139][k]
+            assert small.output(1)[0] == ref[0][k]
+            assert small.output(2)[0] == ref[128][k]
+        small.close()
+    o = make_oracles(fs, blk, [vfos[63]])[0]
+    for k, x in enumerate(xs):
+        assert o.process(x) == ref[63][k]
+
+
+def test_full_rate_wideband_d8_l5_vs_oracle_and_properties():
+    """BASELINE config C geometry (61.44 MS/s cf32, B = Fs/4, D=8, late /5 -> 48 kHz), 64 VFOs.
+    Oracle parity on 3 of them over 2 blocks; for all of them: silence -> zeros, and the bytes of a
+    VFO are identical to those of the same VFO in a 1-VFO bank (first/last column included)."""
+    fs, blk = 61440000, 15360000
+    rng = np.random.default_rng(61)
+    vfos = _mixed_bank(fs, 64, rng, [8], late=5)
+    for v in vfos:
+        v["gain"] = 0.05
+    bank = make_bank(fs, blk, FMT_CF32, vfos)
+    picks = (0, 31, 63)
+    oracles = make_oracles(fs, blk, [vfos[i] for i in picks])
+    digests = {i: [] for i in range(64)}
+    for b in range(2):
+        x = synth_raw(FMT_CF32, b * blk, blk, seed=77, amp=0.5)
+        bank.process(x)
+        for i in range(64):
+            digests[i].append(hashlib.sha256(bank.output(i)[0]).hexdigest())
+        for j, i in enumerate(picks):
+            want = oracles[j].process(x)
+            got, rate = bank.output(i)
+            assert rate == 48000 and len(got) == 24000
+            assert got == want, "VFO %d block %d" % (i, b)
+    bank.close()
+    solo = make_bank(fs, blk, FMT_CF32, [vfos[63]])
+    for b in range(2):
+        solo.process(synth_raw(FMT_CF32, b * blk, blk, seed=77, amp=0.5))
+        assert hashlib.sha256(solo.output(0)[0]).hexdigest() == digests[63][b]
+    solo.close()
+    assert len({tuple(v) for v in digests.values()}) == 64   # every VFO produced its own stream
