@@ -42,7 +42,7 @@ ABI_SYMBOLS = [
     "aeroddc_bank_output", "aeroddc_bank_topic", "aeroddc_bank_stage_d", "aeroddc_bank_num_vfos",
     "aeroddc_bank_last_timing", "aeroddc_bank_last_main_ms", "aeroddc_bank_device_bytes",
     "aeroddc_bank_destroy", "aeroddc_last_error", "aeroddc_measure_fp32_peak", "aeroddc_abi_version",
-    "aeroddc_design_lowpass", "aeroddc_design_hilbert", "aeroddc_design_rotation",
+    "aeroddc_design_lowpass", "aeroddc_design_hilbert", "aeroddc_design_rotation", "aeroddc_bank_stopwatch",
 ]
 
 _lib = None
@@ -73,6 +73,7 @@ def lib():
         L.aeroddc_bank_last_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ci)]
         L.aeroddc_bank_last_main_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
         L.aeroddc_bank_device_bytes.argtypes = [vp, ctypes.POINTER(cz)]
+        L.aeroddc_bank_stopwatch.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_float)]
         L.aeroddc_bank_destroy.argtypes = [vp]
         L.aeroddc_bank_destroy.restype = None
         L.aeroddc_last_error.restype = ctypes.c_char_p
@@ -191,6 +192,14 @@ class Bank:
     def last_main_ms(self):
         ms = ctypes.c_float()
         _check(self._L.aeroddc_bank_last_main_ms(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    def stopwatch_start(self, host_inputs=False):
+        _check(self._L.aeroddc_bank_stopwatch(self._h, 1 if host_inputs else 0, None))
+
+    def stopwatch_stop(self):
+        ms = ctypes.c_float()
+        _check(self._L.aeroddc_bank_stopwatch(self._h, 2, ctypes.byref(ms)))
         return ms.value
 
     def device_bytes(self):

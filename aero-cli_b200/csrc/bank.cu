@@ -92,6 +92,7 @@ struct aeroddc_bank {
 
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
   cudaEvent_t ev_h2d[2] = {};
+  cudaEvent_t ev_sw0 = nullptr, ev_sw1 = nullptr;
   cudaEvent_t ev_done[3] = {}, ev_k0[3] = {}, ev_k1[3] = {}, ev_m0[3] = {}, ev_m1[3] = {};
 
   long long blocks_submitted = 0, blocks_done = 0;
@@ -149,6 +150,8 @@ void free_all(aeroddc_bank* b) {
     if (b->ev_m0[i]) cudaEventDestroy(b->ev_m0[i]);
     if (b->ev_m1[i]) cudaEventDestroy(b->ev_m1[i]);
   }
+  if (b->ev_sw0) cudaEventDestroy(b->ev_sw0);
+  if (b->ev_sw1) cudaEventDestroy(b->ev_sw1);
   if (b->s_compute) cudaStreamDestroy(b->s_compute);
   if (b->s_copy) cudaStreamDestroy(b->s_copy);
 }
@@ -413,6 +416,8 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
     CU(cudaEventCreate(&b->ev_m0[i])); CU(cudaEventCreate(&b->ev_m1[i]));
     CU(cudaEventCreateWithFlags(&b->ev_done[i], cudaEventDisableTiming));
   }
+  CU(cudaEventCreate(&b->ev_sw0));
+  CU(cudaEventCreate(&b->ev_sw1));
   CU(cudaStreamCreateWithFlags(&b->s_compute, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&b->s_copy, cudaStreamNonBlocking));
 
@@ -537,6 +542,18 @@ int aeroddc_bank_last_timing(aeroddc_bank* b, float* kernel_ms, int* launches) {
 int aeroddc_bank_last_main_ms(aeroddc_bank* b, float* main_ms) {
   if (!b) return fail(AERODDC_ERR_ARG, "NULL bank");
   if (main_ms) *main_ms = b->last_main_ms;
+  return AERODDC_OK;
+}
+int aeroddc_bank_stopwatch(aeroddc_bank* b, int which, float* ms) {
+  if (!b) return fail(AERODDC_ERR_ARG, "NULL bank");
+  if (!b->finalized) return fail(AERODDC_ERR_STATE, "bank not finalized");
+  CU(cudaSetDevice(b->device));
+  if (which == 0) { CU(cudaEventRecord(b->ev_sw0, b->s_compute)); return AERODDC_OK; }
+  if (which == 1) { CU(cudaEventRecord(b->ev_sw0, b->s_copy)); return AERODDC_OK; }
+  if (which != 2 || !ms) return fail(AERODDC_ERR_ARG, "which must be 0, 1 or 2 (with ms)");
+  CU(cudaEventRecord(b->ev_sw1, b->s_compute));
+  CU(cudaEventSynchronize(b->ev_sw1));
+  CU(cudaEventElapsedTime(ms, b->ev_sw0, b->ev_sw1));
   return AERODDC_OK;
 }
 int aeroddc_bank_device_bytes(aeroddc_bank* b, size_t* bytes) {

@@ -116,6 +116,13 @@ int aeroddc_bank_last_timing(aeroddc_bank *bank, float *kernel_ms, int *launches
 /* Device time of the dominant kernel (the fused unpack + mix + half-band cascade) alone. */
 int aeroddc_bank_last_main_ms(aeroddc_bank *bank, float *main_ms);
 
+/* Stopwatch on the bank's own streams, for measuring several blocks as one region with CUDA events:
+ * which = 0 records the start event on the compute stream (inputs already in HBM),
+ * which = 1 records the start event on the copy stream (host inputs; the H2D copies are inside),
+ * which = 2 records the stop event on the compute stream, waits for it, and returns the elapsed
+ * milliseconds since the last start in *ms. */
+int aeroddc_bank_stopwatch(aeroddc_bank *bank, int which, float *ms);
+
 /* Resource use after finalize: bytes of HBM held by the bank. */
 int aeroddc_bank_device_bytes(aeroddc_bank *bank, size_t *bytes);
 
