@@ -32,6 +32,7 @@ class VfoDesc(ctypes.Structure):
         ("compress_style", ctypes.c_int),
         ("scale_comp", ctypes.c_int),
         ("topic", ctypes.c_char * 64),
+        ("parent", ctypes.c_int),
     ]
 
 
@@ -129,9 +130,9 @@ class Bank:
         _check(self._L.aeroddc_bank_create(ctypes.byref(self._h), sample_rate, block_len, in_format, device))
 
     def add_vfo(self, mixer_freq, decim_count, late_decimate=0, filter_bw=0, gain=0.01, demod_usb=1,
-                compress_style=1, scale_comp=1, topic=""):
+                compress_style=1, scale_comp=1, topic="", parent=-1):
         d = VfoDesc(float(mixer_freq), int(decim_count), int(late_decimate), int(filter_bw), float(gain),
-                    int(demod_usb), int(compress_style), int(scale_comp), topic.encode()[:63])
+                    int(demod_usb), int(compress_style), int(scale_comp), topic.encode()[:63], int(parent))
         return _check(self._L.aeroddc_bank_add_vfo(self._h, ctypes.byref(d)))
 
     def finalize(self):

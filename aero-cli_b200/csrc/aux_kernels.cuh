@@ -15,10 +15,11 @@ namespace aeroddc {
 // stores the state after every `stride` steps: ckpt[k][v] = state after k*stride steps (k = 0 is
 // (1,0)), i.e. the value from which one more step yields table entry q[k*stride]. qlast = q[L-1].
 // ---------------------------------------------------------------------------------------------
-__global__ void nco_checkpoint_kernel(const float2* __restrict__ rot, float2* __restrict__ ckpt,
-                                      float2* __restrict__ qlast, int n_vfo, int vfo_pitch, int L, int stride) {
+__global__ void nco_checkpoint_kernel(const float2* __restrict__ rot, const int* __restrict__ nco_len, float2* __restrict__ ckpt,
+                                      float2* __restrict__ qlast, int n_vfo, int vfo_pitch, int stride) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n_vfo) return;
+  const int L = nco_len[v];   // (int)Fs of the stream this VFO mixes (a sub-VFO runs at its parent's output rate)
   const float c = rot[v].x, d = rot[v].y;
   float a = 1.0f, b = 0.0f;
   int k = 0;
@@ -53,6 +54,7 @@ struct TailVfo {
   const float* usb_taps;
   const float* hil_taps;
   int n_stage, n_out;
+  int hist;              // stage-D samples kept in front of the block
   int late, T, U;
   int demod_usb, cstyle, scalecomp;
   float gain;
@@ -162,8 +164,9 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(const TailVfo* __res
 // Keep the last `hist` stage-D samples of every VFO in front of its next block: row[i] = row[n_stage + i],
 // i < hist. Source and destination overlap when n_stage < hist; moving forward in chunks with the
 // whole chunk read before any of it is written keeps that safe (dst < src).
-__global__ void __launch_bounds__(256) xd_shift_kernel(const TailVfo* __restrict__ vfos, int hist) {
+__global__ void __launch_bounds__(256) xd_shift_kernel(const TailVfo* __restrict__ vfos) {
   const TailVfo v = vfos[blockIdx.x];
+  const int hist = v.hist;
   float2* row = const_cast<float2*>(v.xd) - hist;
   for (int base = 0; base < hist; base += 1024) {
     float2 r[4];

@@ -42,15 +42,20 @@ using namespace aeroddc;
 struct VfoRec {
   aeroddc_vfo_desc d;
   TailPlan plan;
-  int slot;          // column in the device tables (VFOs are grouped by decimation count)
+  int fs_in, blk_in; // rate and block length of the stream this VFO mixes (the raw IQ, or its parent's output)
+  int children;      // number of VFOs fed by this one (> 0: publishes nothing itself, vfo.cpp:167-172)
+  int slot;          // column in the device tables (VFOs are grouped by input stream and decimation count)
   int hist;          // stage-D history samples kept in front of each block
+  size_t xd_off;     // float2 offset of this VFO's row (history first) in d_xd
   size_t out_bytes;  // payload bytes per block
   size_t out_off;    // offset of the payload row in the output buffers
   size_t taps_off[3];
 };
 
-struct Group {   // VFOs sharing D: one launch of the main kernel per block
+struct Group {   // VFOs sharing input stream and D: one launch of the main kernel per block
+  int parent;      // -1: raw IQ of the bank; else the VFO whose stage-D stream is the input
   int D, base, count;
+  int fs_in, blk_in;
   int S, W, Wb, nseg;
 };
 
@@ -76,8 +81,10 @@ struct aeroddc_bank {
   // device memory
   float2 *d_rot = nullptr, *d_qlast = nullptr, *d_ckpt = nullptr;
   float2* d_state[2] = {nullptr, nullptr};
-  float2* d_xd = nullptr;       // [vfo_pitch][xd_pitch]
-  int xd_pitch = 0, hist_max = 0, nstage_max = 0;
+  float2* d_xd = nullptr;       // all stage-D rows, per VFO: [hist][n_stage]
+  float2** d_xd_rows = nullptr; // [vfo_pitch] pointer to stage-D index 0 of each column's row
+  int* d_nco_len = nullptr;     // [vfo_pitch]
+  int nck_max = 0;
   float* d_taps = nullptr;
   TailVfo* d_tail = nullptr;
   unsigned char* d_out = nullptr;
@@ -102,6 +109,7 @@ struct aeroddc_bank {
   int launches_per_block = 0;
   size_t tail_smem = 0;
   int tail_chunks = 0;
+  bool any_hist = false;
 };
 
 namespace {
@@ -136,7 +144,7 @@ void free_all(aeroddc_bank* b) {
   if (b->s_copy) cudaStreamSynchronize(b->s_copy);
   cudaFree(b->d_rot); cudaFree(b->d_qlast); cudaFree(b->d_ckpt);
   cudaFree(b->d_state[0]); cudaFree(b->d_state[1]);
-  cudaFree(b->d_xd); cudaFree(b->d_taps); cudaFree(b->d_tail); cudaFree(b->d_out);
+  cudaFree(b->d_xd); cudaFree(b->d_xd_rows); cudaFree(b->d_nco_len); cudaFree(b->d_taps); cudaFree(b->d_tail); cudaFree(b->d_out);
   cudaFree(b->d_in[0]); cudaFree(b->d_in[1]);
   for (int i = 0; i < 2; ++i) {
     if (b->h_in[i]) cudaFreeHost(b->h_in[i]);
@@ -160,36 +168,34 @@ void free_all(aeroddc_bank* b) {
 int enqueue_block(aeroddc_bank* b, const void* dev_iq) {
   const int slot = (int)(b->blocks_submitted % 3);   // payload/event slot
   cudaStream_t s = b->s_compute;
-  const long long block_abs = b->blocks_submitted * (long long)b->B;
   const int par = (int)(b->blocks_submitted & 1);
   int launches = 0;
   CU(cudaEventRecord(b->ev_k0[slot], s));
   CU(cudaEventRecord(b->ev_m0[slot], s));
   for (const Group& g : b->groups) {
     MainParams p;
-    p.iq = dev_iq;
+    // a sub-VFO group reads its parent's stage-D stream of this block (already enqueued on this stream)
+    p.iq = g.parent < 0 ? dev_iq : (const void*)(b->d_xd + b->vfos[g.parent].xd_off + b->vfos[g.parent].hist);
     p.ckpt = b->d_ckpt;
     p.rot = b->d_rot;
     p.qlast = b->d_qlast;
     p.state_in = b->d_state[par];
     p.state_out = b->d_state[par ^ 1];
-    p.xd = b->d_xd;
-    p.block_abs = block_abs;
-    p.xd_pitch = b->xd_pitch;
-    p.xd_hist = b->hist_max;
+    p.xd_rows = b->d_xd_rows;
+    p.block_abs = b->blocks_submitted * (long long)g.blk_in;
     p.vfo_pitch = b->vfo_pitch;
     p.vfo_base = g.base;
     p.vfo_count = g.count;
     p.D = g.D;
-    p.B = b->B;
+    p.B = g.blk_in;
     p.S = g.S;
     p.W = g.W;
     p.nseg = g.nseg;
     p.Wb = g.Wb;
-    p.nco_len = b->fs;
+    p.nco_len = g.fs_in;
     p.one = 1.0f;
     dim3 grid(g.nseg + 1, (g.count + kVfoPerCta - 1) / kVfoPerCta);
-    CU(launch_main(b->fmt, std::min(g.D, kFastStages), p, grid, s));
+    CU(launch_main(g.parent < 0 ? b->fmt : AERODDC_CF32, std::min(g.D, kFastStages), p, grid, s));
     ++launches;
   }
   CU(cudaEventRecord(b->ev_m1[slot], s));
@@ -201,8 +207,8 @@ int enqueue_block(aeroddc_bank* b, const void* dev_iq) {
   }
   CU(cudaEventRecord(b->ev_k1[slot], s));
   // keep the last hist_max stage-D samples of every VFO in front of the next block
-  if (b->hist_max > 0) {
-    xd_shift_kernel<<<(unsigned)b->vfos.size(), 256, 0, s>>>(b->d_tail, b->hist_max);
+  if (b->any_hist) {
+    xd_shift_kernel<<<(unsigned)b->vfos.size(), 256, 0, s>>>(b->d_tail);
     CU(cudaGetLastError());
     ++launches;
   }
@@ -266,26 +272,40 @@ int aeroddc_bank_add_vfo(aeroddc_bank* b, const aeroddc_vfo_desc* d) {
   if (b->finalized) return fail(AERODDC_ERR_STATE, "bank already finalized");
   if (d->decim_count < 0 || d->decim_count > kMaxStages)
     return fail(AERODDC_ERR_ARG, "decim_count %d outside 0..8 (vfo.h:63)", d->decim_count);
-  const int step = ilcm(kChunk, 1 << d->decim_count);
-  if (b->B % step) return fail(AERODDC_ERR_ARG, "block_len %d not a multiple of %d for D=%d", b->B, step, d->decim_count);
-  if (d->decim_count > 0 && b->B < 20 * (1 << d->decim_count))
-    return fail(AERODDC_ERR_ARG, "block_len %d too short for D=%d (need >= %d)", b->B, d->decim_count, 20 << d->decim_count);
-  const int late = d->demod_usb ? d->late_decimate : 0;
-  if (late < 0 || late == 1) return fail(AERODDC_ERR_ARG, "late_decimate must be 0 or >= 2");
-  const int n_stage = b->B >> d->decim_count;
-  if (late > 0 && n_stage % late) return fail(AERODDC_ERR_ARG, "stage-D block %d not divisible by late_decimate %d", n_stage, late);
   VfoRec r;
   r.d = *d;
   r.d.topic[sizeof r.d.topic - 1] = 0;
+  r.children = 0;
+  if (d->parent >= (int)b->vfos.size() || d->parent < -1) return fail(AERODDC_ERR_ARG, "parent %d is not an earlier VFO", d->parent);
+  if (d->parent >= 0) {
+    const VfoRec& pr = b->vfos[d->parent];
+    if (pr.d.parent >= 0) return fail(AERODDC_ERR_ARG, "only one level of main -> sub VFOs (publisher.cpp:118-219)");
+    r.fs_in = (int)(pr.fs_in / std::pow(2.0, pr.d.decim_count));   // vfo::getOutRate (vfo.cpp:147)
+    r.blk_in = pr.plan.n_stage;
+  } else {
+    r.fs_in = b->fs;
+    r.blk_in = b->B;
+  }
+  const int step = ilcm(kChunk, 1 << d->decim_count);
+  if (r.blk_in % step) return fail(AERODDC_ERR_ARG, "input block %d not a multiple of %d for D=%d", r.blk_in, step, d->decim_count);
+  if (d->decim_count > 0 && r.blk_in < 20 * (1 << d->decim_count))
+    return fail(AERODDC_ERR_ARG, "input block %d too short for D=%d (need >= %d)", r.blk_in, d->decim_count, 20 << d->decim_count);
+  if (r.blk_in > r.fs_in) return fail(AERODDC_ERR_ARG, "input block %d longer than its rate %d (dsp.cpp:43)", r.blk_in, r.fs_in);
+  const int late = d->demod_usb ? d->late_decimate : 0;
+  if (late < 0 || late == 1) return fail(AERODDC_ERR_ARG, "late_decimate must be 0 or >= 2");
+  const int n_stage = r.blk_in >> d->decim_count;
+  if (late > 0 && n_stage % late) return fail(AERODDC_ERR_ARG, "stage-D block %d not divisible by late_decimate %d", n_stage, late);
   if (r.d.scale_comp <= 0) r.d.scale_comp = 1;
-  if (!plan_tail(b->fs, b->B, d->decim_count, late, d->filter_bw, d->demod_usb != 0, &r.plan))
-    return fail(AERODDC_ERR_DESIGN, "filter design rejected (fs=%d D=%d late=%d bw=%d)", b->fs, d->decim_count, late, d->filter_bw);
+  if (!plan_tail(r.fs_in, r.blk_in, d->decim_count, late, d->filter_bw, d->demod_usb != 0, &r.plan))
+    return fail(AERODDC_ERR_DESIGN, "filter design rejected (fs=%d D=%d late=%d bw=%d)", r.fs_in, d->decim_count, late, d->filter_bw);
   if (r.plan.n_out < 1) return fail(AERODDC_ERR_ARG, "no output samples per block");
   const int T = (int)r.plan.late_taps.size(), U = (int)r.plan.usb_taps.size();
   if (U > 4096) return fail(AERODDC_ERR_ARG, "fir_usb with %d taps is not supported (max 4096)", U);
   r.hist = d->demod_usb ? (U + kHilbert - 1) * std::max(late, 1) + T : 0;
+  r.hist = (r.hist + 1) & ~1;
   r.out_bytes = d->demod_usb ? (size_t)r.plan.n_out * 2 : (d->compress_style == 1 ? (size_t)r.plan.n_out : (size_t)r.plan.n_out * 2);
   b->vfos.push_back(r);
+  if (d->parent >= 0) b->vfos[d->parent].children++;
   return (int)b->vfos.size() - 1;
 }
 
@@ -299,68 +319,84 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
   if (prop.major < 10) return fail(AERODDC_ERR_CUDA, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
   b->n_sm = prop.multiProcessorCount;
 
-  // ---- group VFOs by D; each group starts at an even column ----
+  // ---- group VFOs by (input stream, D); raw-fed groups first so that parents run before children ----
   const int nv = (int)b->vfos.size();
   int col = 0;
-  for (int D = 0; D <= kMaxStages; ++D) {
-    Group g;
-    g.D = D; g.base = col; g.count = 0;
-    for (int i = 0; i < nv; ++i)
-      if (b->vfos[i].d.decim_count == D) { b->vfos[i].slot = col++; g.count++; }
-    if (!g.count) continue;
-    b->groups.push_back(g);
+  for (int parent = -1; parent < nv; ++parent) {
+    if (parent >= 0 && b->vfos[parent].children == 0) continue;
+    for (int D = 0; D <= kMaxStages; ++D) {
+      Group g;
+      g.parent = parent; g.D = D; g.base = col; g.count = 0;
+      for (int i = 0; i < nv; ++i)
+        if (b->vfos[i].d.parent == parent && b->vfos[i].d.decim_count == D) {
+          b->vfos[i].slot = col++; g.count++;
+          g.fs_in = b->vfos[i].fs_in; g.blk_in = b->vfos[i].blk_in;
+        }
+      if (g.count) b->groups.push_back(g);
+    }
   }
   b->vfo_pitch = (col + 3) & ~3;
   const char* env_waves = getenv("AERODDC_WAVES");
-  const double waves = env_waves ? std::max(0.25, atof(env_waves)) : 1.0;
+  const double waves = env_waves ? std::max(0.05, atof(env_waves)) : 1.0;
   for (Group& g : b->groups) {
     const int align = ilcm(kNcoStride, 1 << g.D);
-    g.W = g.D == 0 ? 0 : ((10 << g.D) + (ilcm(kChunk, 1 << g.D) - 1)) / ilcm(kChunk, 1 << g.D) * ilcm(kChunk, 1 << g.D);
+    const int cstep = ilcm(kChunk, 1 << g.D);
+    g.W = g.D == 0 ? 0 : ((10 << g.D) + cstep - 1) / cstep * cstep;
     g.Wb = g.D == 0 ? 0 : (11 << g.D);
     const int nblk_y = (g.count + kVfoPerCta - 1) / kVfoPerCta;
     const int target = std::max(1, (int)std::floor((double)kCtasPerSm * b->n_sm * waves / nblk_y) - 1);   // -1: the boundary CTA
-    int S = (b->B + target - 1) / target;
+    int S = (g.blk_in + target - 1) / target;
     S = std::max(S, std::max(4 * g.W, 4096));
     S = (S + align - 1) / align * align;
     g.S = S;
-    g.nseg = (b->B + S - 1) / S;
+    g.nseg = (g.blk_in + S - 1) / S;
   }
 
   // ---- constant tables ----
   std::vector<float2> h_rot(b->vfo_pitch, make_float2(1.0f, 0.0f));
-  for (const VfoRec& r : b->vfos) design_rotation((double)b->fs, r.d.mixer_freq, &h_rot[r.slot].x, &h_rot[r.slot].y);
-  b->nck = (b->fs + kNcoStride - 1) / kNcoStride;
+  std::vector<int> h_len(b->vfo_pitch, 1);
+  b->nck_max = 1;
+  for (const VfoRec& r : b->vfos) {
+    design_rotation((double)r.fs_in, r.d.mixer_freq, &h_rot[r.slot].x, &h_rot[r.slot].y);
+    h_len[r.slot] = r.fs_in;
+    b->nck_max = std::max(b->nck_max, (r.fs_in + kNcoStride - 1) / kNcoStride);
+  }
   size_t bytes = 0;
   auto dmalloc = [&](void** p, size_t n) { bytes += n; return cudaMalloc(p, n); };
   CU(dmalloc((void**)&b->d_rot, sizeof(float2) * b->vfo_pitch));
   CU(dmalloc((void**)&b->d_qlast, sizeof(float2) * b->vfo_pitch));
-  CU(dmalloc((void**)&b->d_ckpt, sizeof(float2) * (size_t)b->nck * b->vfo_pitch));
-  CU(cudaMemset(b->d_ckpt, 0, sizeof(float2) * (size_t)b->nck * b->vfo_pitch));
+  CU(dmalloc((void**)&b->d_nco_len, sizeof(int) * b->vfo_pitch));
+  CU(dmalloc((void**)&b->d_ckpt, sizeof(float2) * (size_t)b->nck_max * b->vfo_pitch));
+  CU(cudaMemset(b->d_ckpt, 0, sizeof(float2) * (size_t)b->nck_max * b->vfo_pitch));
   CU(cudaMemset(b->d_qlast, 0, sizeof(float2) * b->vfo_pitch));
   CU(cudaMemcpy(b->d_rot, h_rot.data(), sizeof(float2) * b->vfo_pitch, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(b->d_nco_len, h_len.data(), sizeof(int) * b->vfo_pitch, cudaMemcpyHostToDevice));
   for (int i = 0; i < 2; ++i) {
     const size_t n = sizeof(float2) * (size_t)kMaxStages * kStateSlots * b->vfo_pitch;
     CU(dmalloc((void**)&b->d_state[i], n));
     CU(cudaMemset(b->d_state[i], 0, n));   // first block: all-zero history (dsp.cpp:48-52)
   }
 
-  // ---- stage-D stream and payload rows ----
-  b->hist_max = 0; b->nstage_max = 0;
-  size_t taps_total = 0, out_off = 0;
+  // ---- stage-D rows and payload rows ----
+  size_t taps_total = 0, out_off = 0, xd_total = 0;
   for (VfoRec& r : b->vfos) {
-    b->hist_max = std::max(b->hist_max, r.hist);
-    b->nstage_max = std::max(b->nstage_max, r.plan.n_stage);
+    r.xd_off = xd_total;
+    xd_total += ((size_t)r.hist + r.plan.n_stage + 1) & ~(size_t)1;
+    if (r.hist > 0) b->any_hist = true;
     r.taps_off[0] = taps_total; taps_total += r.plan.late_taps.size();
     r.taps_off[1] = taps_total; taps_total += r.plan.usb_taps.size();
     r.taps_off[2] = taps_total; taps_total += r.plan.hilbert_taps.size();
     r.out_off = out_off;
+    if (r.children) r.out_bytes = 0;   // a main VFO with sub-VFOs only feeds them (vfo.cpp:167-172)
     out_off += (r.out_bytes + 15) & ~(size_t)15;
   }
-  b->hist_max = (b->hist_max + 1) & ~1;
-  b->out_total = out_off;
-  b->xd_pitch = ((b->hist_max + b->nstage_max + 1) & ~1);
-  CU(dmalloc((void**)&b->d_xd, sizeof(float2) * (size_t)b->vfo_pitch * b->xd_pitch));
-  CU(cudaMemset(b->d_xd, 0, sizeof(float2) * (size_t)b->vfo_pitch * b->xd_pitch));
+  b->out_total = std::max<size_t>(out_off, 16);
+  CU(dmalloc((void**)&b->d_xd, sizeof(float2) * xd_total));
+  CU(cudaMemset(b->d_xd, 0, sizeof(float2) * xd_total));
+  std::vector<float2*> h_rows(b->vfo_pitch, b->d_xd);
+  for (const VfoRec& r : b->vfos) h_rows[r.slot] = b->d_xd + r.xd_off + r.hist;
+  CU(dmalloc((void**)&b->d_xd_rows, sizeof(float2*) * b->vfo_pitch));
+  CU(cudaMemcpy(b->d_xd_rows, h_rows.data(), sizeof(float2*) * b->vfo_pitch, cudaMemcpyHostToDevice));
   std::vector<float> h_taps(std::max<size_t>(taps_total, 1));
   for (const VfoRec& r : b->vfos) {
     std::copy(r.plan.late_taps.begin(), r.plan.late_taps.end(), h_taps.begin() + r.taps_off[0]);
@@ -377,13 +413,14 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
   for (int i = 0; i < nv; ++i) {
     const VfoRec& r = b->vfos[i];
     TailVfo& t = h_tail[i];
-    t.xd = b->d_xd + (size_t)r.slot * b->xd_pitch + b->hist_max;
+    t.xd = b->d_xd + r.xd_off + r.hist;
     t.out = b->d_out + r.out_off;
     t.late_taps = b->d_taps + r.taps_off[0];
     t.usb_taps = b->d_taps + r.taps_off[1];
     t.hil_taps = b->d_taps + r.taps_off[2];
     t.n_stage = r.plan.n_stage;
-    t.n_out = r.plan.n_out;
+    t.n_out = r.children ? 0 : r.plan.n_out;
+    t.hist = r.hist;
     t.late = r.plan.late;
     t.T = (int)r.plan.late_taps.size();
     t.U = (int)r.plan.usb_taps.size();
@@ -397,7 +434,7 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
     tail_smem = std::max(tail_smem, sm);
   }
   b->tail_smem = tail_smem;
-  b->tail_chunks = (max_out + kTailChunk - 1) / kTailChunk;
+  b->tail_chunks = std::max(1, (max_out + kTailChunk - 1) / kTailChunk);
   CU(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
   CU(dmalloc((void**)&b->d_tail, sizeof(TailVfo) * nv));
   CU(cudaMemcpy(b->d_tail, h_tail.data(), sizeof(TailVfo) * nv, cudaMemcpyHostToDevice));
@@ -425,7 +462,7 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
   {
     const int threads = 32;
     nco_checkpoint_kernel<<<(b->vfo_pitch + threads - 1) / threads, threads, 0, b->s_compute>>>(
-        b->d_rot, b->d_ckpt, b->d_qlast, b->vfo_pitch, b->vfo_pitch, b->fs, kNcoStride);
+        b->d_rot, b->d_nco_len, b->d_ckpt, b->d_qlast, b->vfo_pitch, b->vfo_pitch, kNcoStride);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(b->s_compute));
   }
@@ -521,13 +558,11 @@ int aeroddc_bank_stage_d(aeroddc_bank* b, int vfo, float* host_out, size_t cap_c
   if (b->blocks_done < 1 || b->blocks_done != b->blocks_submitted) return fail(AERODDC_ERR_STATE, "needs a completed block and nothing in flight");
   CU(cudaSetDevice(b->device));
   const VfoRec& r = b->vfos[vfo];
-  // after the history shift the block occupies [hist_max - n_stage_max + ..]: read it back relative to the end
   const size_t n = std::min<size_t>(cap_complex, (size_t)r.plan.n_stage);
-  const float2* row = b->d_xd + (size_t)r.slot * b->xd_pitch;
-  // the last n_stage samples of this VFO were at [hist_max, hist_max + n_stage); the shift moved
-  // [nstage_max, nstage_max + hist_max) to the front, so only rows still in place are readable here
+  // the block stays at [hist, hist + n_stage) of the row until the next block overwrites it; the
+  // history shift only rewrites [0, hist)
   CU(cudaStreamSynchronize(b->s_compute));
-  CU(cudaMemcpy(host_out, row + b->hist_max, n * sizeof(float2), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(host_out, b->d_xd + r.xd_off + r.hist, n * sizeof(float2), cudaMemcpyDeviceToHost));
   return (int)r.plan.n_stage;
 }
 

@@ -109,9 +109,8 @@ struct MainParams {
   const float2* qlast;       // [vfo_pitch] q[L-1], the value sample 0 is mixed with
   const float2* state_in;    // [kMaxStages][kStateSlots][vfo_pitch] history at the start of this block
   float2* state_out;         // same layout, history for the start of the next block
-  float2* xd;                // [vfo_pitch][xd_pitch] stage-D stream; this block goes to [xd_hist, xd_hist+B>>D)
+  float2* const* xd_rows;    // [vfo_pitch] per VFO: where stage-D sample 0 of this block goes (history lies in front)
   long long block_abs;       // absolute index of the block's first sample
-  int xd_pitch, xd_hist;
   int vfo_pitch;             // padded VFO count (row pitch of ckpt/rot/state)
   int vfo_base, vfo_count;   // VFO slice handled by this launch (all share D)
   int D;                     // half-band stages
@@ -403,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
   }
 
   // stage-D output cursor: outputs before the segment start (warm-up) are discarded
-  float2* xd = p.xd + (size_t)vfo * p.xd_pitch + p.xd_hist;
+  float2* xd = p.xd_rows[vfo];
   const int out_first = seg_start >> p.D;                 // first stage-D index this segment owns
   int out_pos = first >> p.D;                             // stage-D index of the next output produced
   unsigned chunk_ctr = 0;                                 // chunks since `first` (first is 2^D aligned)

@@ -52,6 +52,11 @@ typedef struct aeroddc_vfo_desc {
   int compress_style;  /* vfo::setCompressonStyle: 1 = nibble-packed, 0 = int8 I,Q (demod_usb == 0)  */
   int scale_comp;      /* vfo::setScaleComp (>0)                                                     */
   char topic[64];      /* vfo::setZmqTopic; the wire carries its first 5 bytes (zmqpublisher.cpp:69) */
+  int parent;          /* -1: fed by the bank's raw IQ. Otherwise the index of an earlier VFO (a "main" VFO,
+                          publisher.cpp:118-148) whose stage-D stream is this VFO's input, as vfo::setVFOs
+                          + the recursion in vfo::process do (vfo.cpp:167-172). A VFO that has children
+                          publishes nothing itself, like the reference. Its children run at its output
+                          rate Fs/2^D with blocks of block_len/2^D samples (publisher.cpp:215-217). */
 } aeroddc_vfo_desc;
 
 /* Create an empty bank for blocks of exactly `block_len` complex samples at rate `sample_rate`

@@ -5,12 +5,13 @@ import os
 
 import numpy as np
 
-from golden.cases import CASES, case_dict
+from golden.cases import CASES, NESTED, case_dict, nested_dict
 from oracle_bind import FMT_CF32, Oracle, fnv1a64, synth_anchor, synth_raw, unpack
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = json.load(open(os.path.join(HERE, "golden", "golden.json")))
 ALL_CASES = [case_dict(c) for c in CASES]
+NESTED_CASES = [nested_dict(c) for c in NESTED]
 
 
 def case_fmt(d):
@@ -66,3 +67,30 @@ def parity_metrics(got_i16, want_i16):
     ps = float((w * w).sum())
     snr = float("inf") if pe == 0 else 10.0 * np.log10(ps / pe)
     return maxerr, snr
+
+
+def run_nested_oracle(d):
+    """Main VFO -> sub-VFOs with the oracle: the main's stage-D stream is the subs' cf32 input block
+    (vfo.cpp:167-172). Returns {topic: [payload per block]}, {topic: rate}."""
+    fm, Dm = d["main"]
+    main = Oracle(d["Fs"], d["B"], Dm, 0, fm, 0.01, 0, 0, 1, 1)
+    fs_sub, blk_sub = d["Fs"] >> Dm, d["B"] >> Dm
+    subs = [Oracle(fs_sub, blk_sub, D, L, f, g, bw) for (f, D, L, g, bw) in d["subs"]]
+    out = {"S%04d" % i: [] for i in range(len(subs))}
+    for b in range(d["blocks"]):
+        main.process(float_block(d, b))
+        mid = main.stage(Dm)
+        for i, s_ in enumerate(subs):
+            out["S%04d" % i].append(s_.process(mid))
+    rates = {"S%04d" % i: s_.out_rate for i, s_ in enumerate(subs)}
+    return out, rates
+
+
+def check_nested_golden(name, out, rates):
+    g = GOLDEN[name]
+    assert sorted(out) == sorted(g)
+    for t, blocks in out.items():
+        assert rates[t] == g[t]["rate"]
+        assert sum(len(b) for b in blocks) == g[t]["bytes"]
+        for i, blk in enumerate(blocks):
+            assert hashlib.sha256(blk).hexdigest() == g[t]["block_sha256"][i], "%s %s block %d differs from the reference" % (name, t, i)

@@ -34,3 +34,24 @@ CASES = [
 def case_dict(c):
     keys = ["name", "Fs", "B", "D", "L", "mixer", "gain", "filter_bw", "demod_usb", "cstyle", "scalecomp", "blocks", "input"]
     return dict(zip(keys, c))
+
+
+# Nested main -> sub topologies as Publisher::loadSettings builds them (publisher.cpp:118-219): the main VFO
+# (demod_usb = 0, compress style 1) only feeds its sub-VFOs, which mix/decimate its stage-D stream at its
+# output rate. (name, Fs, B, main (mixer, D), subs [(mixer, D, L, gain, filter_bw)], blocks, input)
+NESTED = [
+    # config B shape: main at the centre with out_rate = Fs (D = 0), 600/1200/10500-style subs
+    ("nested_1536k_main_d0", 1536000, 384000, (0.0, 0),
+     [(-601234.0, 7, 0, 0.075, 0), (455001.0, 6, 0, 0.05, 0), (123456.0, 5, 0, 0.1, 0), (-33000.0, 7, 0, 0.08, 0)], 5, ("raw", FMT_CF32, 31, 0.6)),
+    # main decimating by 8 to 240 kHz, subs use the late /5 stage (main_out_rate / 48000 == 5)
+    ("nested_1920k_main_d3_late5", 1920000, 480000, (-250000.0, 3),
+     [(20000.0, 0, 5, 0.5, 0), (-61000.5, 0, 5, 0.4, 3000), (7000.0, 1, 5, 0.5, 0)], 5, "anchor"),
+    # main to 288 kHz (late /6), cu8 input
+    ("nested_2304k_main_d3_late6_cu8", 2304000, 576000, (400000.0, 3),
+     [(-30000.0, 0, 6, 0.5, 0), (45000.0, 1, 6, 0.5, 0)], 5, ("raw", FMT_CU8, 32, 0.8)),
+]
+
+
+def nested_dict(c):
+    keys = ["name", "Fs", "B", "main", "subs", "blocks", "input"]
+    return dict(zip(keys, c))

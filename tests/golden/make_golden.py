@@ -18,7 +18,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 from oracle_bind import RefVfo, fnv1a64, ref_lib, synth_anchor, synth_raw, unpack  # noqa: E402
-from golden.cases import CASES, case_dict  # noqa: E402
+from golden.cases import CASES, NESTED, case_dict, nested_dict  # noqa: E402
 
 
 def block_input(spec, n0, n):
@@ -55,6 +55,27 @@ def main():
         }
         print(d["name"], len(allb), out[d["name"]]["fnv1a64"], rate)
         r.close()
+    for c in NESTED:
+        d = nested_dict(c)
+        fm, Dm = d["main"]
+        main = RefVfo(d["Fs"], d["B"], Dm, 0, fm, 0.01, 0, 0, 1, 1, topic="MAIN0")   # publisher.cpp:136-147
+        fs_sub, blk_sub = d["Fs"] >> Dm, d["B"] >> Dm
+        subs = []
+        for i, (f, D, L, g, bw) in enumerate(d["subs"]):
+            s_ = RefVfo(fs_sub, blk_sub, D, L, f, g, bw, 1, 1, 1, topic="S%04d" % i)     # publisher.cpp:196-217
+            main.add_sub(s_)
+            subs.append(s_)
+        per = {s_.topic: {"block_sha256": [], "rate": 0, "bytes": 0} for s_ in subs}
+        for b in range(d["blocks"]):
+            msgs = main.process(block_input(d["input"], b * d["B"], d["B"]))
+            assert "MAIN0" not in msgs          # a main VFO with sub-VFOs publishes nothing itself (vfo.cpp:167-172)
+            for t, (rate, payload) in msgs.items():
+                per[t]["block_sha256"].append(hashlib.sha256(payload).hexdigest())
+                per[t]["rate"] = rate
+                per[t]["bytes"] += len(payload)
+        out[d["name"]] = per
+        print(d["name"], {t: (v["rate"], v["bytes"]) for t, v in per.items()})
+        main.close()
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
 

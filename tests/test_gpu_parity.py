@@ -10,7 +10,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from case_util import ALL_CASES, case_fmt, check_against_golden, float_block, parity_metrics, raw_block
+from case_util import ALL_CASES, NESTED_CASES, case_fmt, check_against_golden, check_nested_golden, float_block, parity_metrics, raw_block
 from oracle_bind import FMT_CF32, FMT_CS16, FMT_CU8, Oracle, synth_anchor, synth_raw, unpack
 
 pytestmark = pytest.mark.gpu
@@ -49,6 +49,28 @@ def test_golden_cases_byte_identical(d):
         blocks.append(payload)
     stage = bank.stage_d(0, d["B"] >> d["D"])
     check_against_golden(d["name"], blocks, stage, rate)
+    bank.close()
+
+
+@pytest.mark.parametrize("d", NESTED_CASES, ids=[c["name"] for c in NESTED_CASES])
+def test_nested_main_sub_topology_byte_identical(d):
+    """Main VFO feeding sub-VFOs (publisher.cpp:118-219, vfo.cpp:167-172) against the reference's bytes."""
+    a = _aeroddc()
+    bank = a.Bank(d["Fs"], d["B"], case_fmt(d), 0)
+    fm, Dm = d["main"]
+    main = bank.add_vfo(fm, Dm, 0, 0, 0.01, 0, 1, 1, "MAIN0")
+    subs = [bank.add_vfo(f, D, L, bw, g, 1, 1, 1, "S%04d" % i, parent=main) for i, (f, D, L, g, bw) in enumerate(d["subs"])]
+    bank.finalize()
+    out = {"S%04d" % i: [] for i in range(len(subs))}
+    rates = {}
+    for b in range(d["blocks"]):
+        bank.process(raw_block(d, b))
+        assert bank.output(main)[0] == b""      # a main VFO with sub-VFOs publishes nothing itself
+        for i, v in enumerate(subs):
+            payload, rate = bank.output(v)
+            out["S%04d" % i].append(payload)
+            rates["S%04d" % i] = rate
+    check_nested_golden(d["name"], out, rates)
     bank.close()
 
 

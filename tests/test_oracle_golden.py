@@ -6,7 +6,7 @@ further seeded configurations and per component (filter designs, NCO table)."""
 import numpy as np
 import pytest
 
-from case_util import ALL_CASES, check_against_golden, float_block, run_oracle
+from case_util import ALL_CASES, NESTED_CASES, check_against_golden, check_nested_golden, float_block, run_nested_oracle, run_oracle
 from oracle_bind import Oracle, RefVfo, oracle_lib, ref_lib
 
 SURVEY_ANCHORS = {
@@ -27,6 +27,12 @@ def test_oracle_matches_reference_golden(d):
         fnv, last6 = SURVEY_ANCHORS[d["name"]]
         assert "%016x" % fnv1a64(b"".join(blocks)) == fnv
         assert list(np.frombuffer(blocks[-1], np.int16)[:6]) == last6
+
+
+@pytest.mark.parametrize("d", NESTED_CASES, ids=[c["name"] for c in NESTED_CASES])
+def test_oracle_nested_matches_reference_golden(d):
+    out, rates = run_nested_oracle(d)
+    check_nested_golden(d["name"], out, rates)
 
 
 def test_oracle_rejects_contract_violations():
