@@ -226,7 +226,9 @@ def main():
 
     # ---- bank: this rank's VFO shard (v mod world) ----
     freqs = vfo_freqs(args.vfos)
-    mine = [v for v in range(args.vfos) if v % world == rank]
+    from aeroddc.shard import shard_vfos
+
+    mine = shard_vfos(args.vfos, world, rank)
     bank = aeroddc.Bank(FS, BLOCK, aeroddc.CF32, local_rank)
     for v in mine:
         bank.add_vfo(float(freqs[v]), DECIM, LATE, 0, GAIN, 1, 1, 1, "V%04d" % v)
