@@ -129,7 +129,8 @@ cudaError_t launch_main_f(int nf, const MainParams& p, dim3 grid, cudaStream_t s
     case 1: return launch_main_t<1, FMT>(p, grid, s);
     case 2: return launch_main_t<2, FMT>(p, grid, s);
     case 3: return launch_main_t<3, FMT>(p, grid, s);
-    default: return launch_main_t<4, FMT>(p, grid, s);
+    case 4: return launch_main_t<4, FMT>(p, grid, s);
+    default: return launch_main_t<5, FMT>(p, grid, s);
   }
 }
 cudaError_t launch_main(int fmt, int nf, const MainParams& p, dim3 grid, cudaStream_t s) {
@@ -344,7 +345,13 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
     g.W = g.D == 0 ? 0 : ((10 << g.D) + cstep - 1) / cstep * cstep;
     g.Wb = g.D == 0 ? 0 : (11 << g.D);
     const int nblk_y = (g.count + kVfoPerCta - 1) / kVfoPerCta;
-    const int target = std::max(1, (int)std::floor((double)kCtasPerSm * b->n_sm * waves / nblk_y) - 1);   // -1: the boundary CTA
+    // One wave of CTAs (kCtasPerSm per SM) is the minimum. The warp scheduler favours some resident warps, so the
+    // CTAs of a single wave finish at different times and the SMs idle at the end; more, shorter segments even
+    // that out at the price of one warm-up (W samples) each. Use up to 4 waves while warm-up stays under ~5 %.
+    const int one_wave = std::max(1, (int)std::floor((double)kCtasPerSm * b->n_sm / nblk_y) - 1);   // -1: the boundary CTA
+    double w = waves;
+    if (!env_waves && g.W > 0) w = std::min(4.0, std::max(1.0, std::floor((double)g.blk_in / one_wave / (20.0 * g.W))));
+    const int target = std::max(1, (int)std::floor((double)kCtasPerSm * b->n_sm * w / nblk_y) - 1);
     int S = (g.blk_in + target - 1) / target;
     S = std::max(S, std::max(4 * g.W, 4096));
     S = (S + align - 1) / align * align;

@@ -23,10 +23,10 @@ namespace aeroddc {
 
 constexpr int kThreads = 128;          // threads per CTA; each thread carries one VFO
 constexpr int kVfoPerCta = kThreads;
-constexpr int kChunk = 16;             // input samples per unrolled inner step
+constexpr int kChunk = 32;             // input samples per unrolled inner step
 constexpr int kTile = 256;             // input samples per shared-memory tile
 constexpr int kMaxStages = 8;          // hdecimator[8], vfo.h:63
-constexpr int kFastStages = 4;         // half-band stages kept in registers
+constexpr int kFastStages = 5;         // half-band stages kept in registers
 constexpr int kStateSlots = 8;         // per stage: 5 even-phase + 3 odd-phase history samples
 constexpr int kNcoStride = 256;        // NCO checkpoint spacing (samples)
 constexpr int kCtasPerSm = 4;          // 16 resident warps per SM at <= 128 registers per thread
@@ -177,36 +177,14 @@ __device__ __forceinline__ void fast_chunk(const Ones& k1, float& oa, float& ob,
     x0[i] = mix(k1, a, b, s);
   }
   if (!SPECIAL) idx += kChunk;
-  if (NF == 0) {
+  // NF half-band stages, compacting in place (output j overwrites slot j after slots 2j, 2j+1 were read)
 #pragma unroll
-    for (int i = 0; i < kChunk; ++i) out[i >> NF] = x0[i];
-    return;
+  for (int s = 0; s < NF; ++s) {
+#pragma unroll
+    for (int j = 0; j < (kChunk >> (s + 1)); ++j) x0[j] = hb_pair(k1, hb[s], x0[2 * j], x0[2 * j + 1]);
   }
-  P2 x1[kChunk / 2];
 #pragma unroll
-  for (int j = 0; j < kChunk / 2; ++j) x1[j] = hb_pair(k1, hb[0], x0[2 * j], x0[2 * j + 1]);
-  if (NF == 1) {
-#pragma unroll
-    for (int i = 0; i < kChunk / 2; ++i) out[(i * 2) >> NF] = x1[i];
-    return;
-  }
-  P2 x2[kChunk / 4];
-#pragma unroll
-  for (int j = 0; j < kChunk / 4; ++j) x2[j] = hb_pair(k1, hb[NF > 1 ? 1 : 0], x1[2 * j], x1[2 * j + 1]);
-  if (NF == 2) {
-#pragma unroll
-    for (int i = 0; i < kChunk / 4; ++i) out[(i * 4) >> NF] = x2[i];
-    return;
-  }
-  P2 x3[kChunk / 8];
-#pragma unroll
-  for (int j = 0; j < kChunk / 8; ++j) x3[j] = hb_pair(k1, hb[NF > 2 ? 2 : 0], x2[2 * j], x2[2 * j + 1]);
-  if (NF == 3) {
-#pragma unroll
-    for (int i = 0; i < kChunk / 8; ++i) out[(i * 8) >> NF] = x3[i];
-    return;
-  }
-  out[0] = hb_pair(k1, hb[NF > 3 ? 3 : 0], x3[0], x3[1]);
+  for (int i = 0; i < (kChunk >> NF); ++i) out[i] = x0[i];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -428,14 +406,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
       else         fast_chunk<NF, false>(k1, oa, ob, rot, hb, tile + c, out, idx, p.nco_len, n_abs, ql.x, ql.y);
       n_abs += kChunk;
       if (NF < kFastStages) {
-        // D == NF < 4: every fast output is a stage-D sample
+        // D == NF < kFastStages: every fast output is a stage-D sample
 #pragma unroll
         for (int i = 0; i < (kChunk >> NF); ++i) {
           if (out_pos >= out_first && active) store_p2(xd + out_pos, out[i]);
           out_pos++;
         }
       } else {
-        // one stage-4 sample per chunk ripples through the deep stages
+        // one stage-kFastStages sample per chunk ripples through the deep stages
         P2 x = out[0];
         unsigned cc = chunk_ctr;
         int s = 0;
