@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libaeroddc.so")
 
 CU8, CS16, CF32 = 0, 1, 2
+MODE_EXACT, MODE_FAST = 0, 1
 _NP_DTYPE = {CU8: np.uint8, CS16: np.int16, CF32: np.float32}
 
 
@@ -43,7 +44,7 @@ ABI_SYMBOLS = [
     "aeroddc_bank_output", "aeroddc_bank_topic", "aeroddc_bank_stage_d", "aeroddc_bank_num_vfos",
     "aeroddc_bank_last_timing", "aeroddc_bank_last_main_ms", "aeroddc_bank_device_bytes",
     "aeroddc_bank_destroy", "aeroddc_last_error", "aeroddc_measure_fp32_peak", "aeroddc_abi_version",
-    "aeroddc_design_lowpass", "aeroddc_design_hilbert", "aeroddc_design_rotation", "aeroddc_bank_stopwatch",
+    "aeroddc_design_lowpass", "aeroddc_design_hilbert", "aeroddc_design_rotation", "aeroddc_bank_stopwatch", "aeroddc_bank_set_mode",
 ]
 
 _lib = None
@@ -75,6 +76,7 @@ def lib():
         L.aeroddc_bank_last_main_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
         L.aeroddc_bank_device_bytes.argtypes = [vp, ctypes.POINTER(cz)]
         L.aeroddc_bank_stopwatch.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_float)]
+        L.aeroddc_bank_set_mode.argtypes = [vp, ci]
         L.aeroddc_bank_destroy.argtypes = [vp]
         L.aeroddc_bank_destroy.restype = None
         L.aeroddc_last_error.restype = ctypes.c_char_p
@@ -134,6 +136,9 @@ class Bank:
         d = VfoDesc(float(mixer_freq), int(decim_count), int(late_decimate), int(filter_bw), float(gain),
                     int(demod_usb), int(compress_style), int(scale_comp), topic.encode()[:63], int(parent))
         return _check(self._L.aeroddc_bank_add_vfo(self._h, ctypes.byref(d)))
+
+    def set_mode(self, mode):
+        _check(self._L.aeroddc_bank_set_mode(self._h, mode))
 
     def finalize(self):
         _check(self._L.aeroddc_bank_finalize(self._h))

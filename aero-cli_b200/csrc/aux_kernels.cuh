@@ -52,7 +52,9 @@ struct TailVfo {
   unsigned char* out;    // payload row
   const float* late_taps;
   const float* usb_taps;
-  const float* hil_taps;
+  const float* hil_taps;   // the non-zero Hilbert taps, in ascending tap order ...
+  const int* hil_idx;      // ... and their tap indices (every other tap of the 125 is exactly +-0.0f and cannot change a sum)
+  int n_hil;
   int n_stage, n_out;
   int hist;              // stage-D samples kept in front of the block
   int late, T, U;
@@ -81,9 +83,16 @@ __device__ __forceinline__ int to_schar_x86(float v) {
   return (int)(signed char)(unsigned char)((unsigned)i & 0xFFu);
 }
 
-__global__ void __launch_bounds__(kTailThreads) tail_kernel(const TailVfo* __restrict__ vfos) {
+// packed (I,Q) helpers for the late FIR; additions as fma(a, 1.0f, b) with 1.0f a kernel parameter, because
+// ptxas would contract mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (see ddc_kernels.cuh)
+__device__ __forceinline__ unsigned long long tl_pack(float a, float b) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ unsigned long long tl_mul(unsigned long long a, unsigned long long b) { unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ unsigned long long tl_fma(unsigned long long a, unsigned long long b, unsigned long long c) { unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
+__global__ void __launch_bounds__(kTailThreads) tail_kernel(const TailVfo* __restrict__ vfos, float one, size_t out_offset) {
   extern __shared__ __align__(16) unsigned char tsm[];
-  const TailVfo v = vfos[blockIdx.y];
+  TailVfo v = vfos[blockIdx.y];
+  v.out += out_offset;   // payload rows are double-buffered by block parity
   const int k0 = blockIdx.x * kTailChunk;
   if (k0 >= v.n_out) return;
   const int kc = min(kTailChunk, v.n_out - k0);
@@ -105,45 +114,58 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(const TailVfo* __res
     return;
   }
 
-  // shared layout: m[(kHilbert-1) + U + kc] float2 | u[U + kc] float | taps
+  // shared layout: mI[n_m] | mQ[n_m] | u[n_u] | taps | staged stage-D window (late > 0 only)
   const int n_m = (kHilbert - 1) + v.U + kc;
   const int n_u = v.U + kc;
-  float2* m = reinterpret_cast<float2*>(tsm);
-  float* u = reinterpret_cast<float*>(m + n_m);
+  const int n_w = v.late > 0 ? (n_m - 1) * v.late + v.T : 0;   // stage-D samples the late FIR of this chunk reads
+  float* mI = reinterpret_cast<float*>(tsm);
+  float* mQ = mI + n_m;
+  float* u = mQ + n_m;
   float* tl = u + n_u;
   float* tu = tl + v.T;
   float* th = tu + v.U;
+  float2* win = reinterpret_cast<float2*>(th + 2 * kHilbert + ((n_m * 2 + n_u + v.T + v.U) & 1));
   for (int i = tid; i < v.T; i += kTailThreads) tl[i] = v.late_taps[i];
   for (int i = tid; i < v.U; i += kTailThreads) tu[i] = v.usb_taps[i];
-  for (int i = tid; i < kHilbert; i += kTailThreads) th[i] = v.hil_taps[i];
-  __syncthreads();
+  int* thi = reinterpret_cast<int*>(th + kHilbert);
+  for (int i = tid; i < v.n_hil; i += kTailThreads) { th[i] = v.hil_taps[i]; thi[i] = v.hil_idx[i]; }
 
-  // phase 1: m[j] for k = k0 - U - 124 + j
+  // phase 0/1: m[j] for k = kbase + j
   const int kbase = k0 - v.U - (kHilbert - 1);
-  for (int j = tid; j < n_m; j += kTailThreads) {
-    const int k = kbase + j;
-    if (v.late > 0) {
-      const float2* w = v.xd + ((long long)k * v.late - v.T);
-      float ar = 0.0f, ai = 0.0f;
+  if (v.late > 0) {
+    const float2* w0 = v.xd + ((long long)kbase * v.late - v.T);   // coalesced copy of the window
+    for (int i = tid; i < n_w; i += kTailThreads) win[i] = w0[i];
+    __syncthreads();
+    const unsigned long long ONE = tl_pack(one, one);
+    for (int j = tid; j < n_m; j += kTailThreads) {
+      const float2* w = win + j * v.late;
+      unsigned long long acc = 0ull;   // (0.0f, 0.0f)
+#pragma unroll 7
       for (int i = 0; i < v.T; ++i) {
-        const float2 s = w[i];
-        ar = __fadd_rn(ar, __fmul_rn(tl[i], s.x));
-        ai = __fadd_rn(ai, __fmul_rn(tl[i], s.y));
+        const float2 sx = w[i];
+        const float t = tl[i];
+        acc = tl_fma(acc, ONE, tl_mul(tl_pack(sx.x, sx.y), tl_pack(t, t)));   // acc + tl[i]*x, both rails, un-fused
       }
-      m[j] = make_float2(ar, ai);
-    } else {
-      m[j] = v.xd[k];
+      float ar, ai;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(ar), "=f"(ai) : "l"(acc));
+      mI[j] = ar;
+      mQ[j] = ai;
+    }
+  } else {
+    for (int j = tid; j < n_m; j += kTailThreads) {
+      const float2 sx = v.xd[kbase + j];
+      mI[j] = sx.x;
+      mQ[j] = sx.y;
     }
   }
   __syncthreads();
-  // phase 2: u[j] for k = k0 - U + j ; m index of k is k - kbase = j + 124
+  // phase 2: u[j] for k = k0 - U + j ; m index of k is j + 124
   for (int j = tid; j < n_u; j += kTailThreads) {
-    const int mi = j + (kHilbert - 1);
     float h = 0.0f;
-    const float2* w = m + (mi - (kHilbert - 1));
-#pragma unroll 5
-    for (int i = 0; i < kHilbert; ++i) h = __fadd_rn(h, __fmul_rn(th[i], w[i].y));
-    u[j] = __fsub_rn(m[mi - kDelay].x, h);
+    const float* w = mQ + j;
+#pragma unroll 7
+    for (int i = 0; i < v.n_hil; ++i) h = __fadd_rn(h, __fmul_rn(th[i], w[thi[i]]));
+    u[j] = __fsub_rn(mI[j + (kHilbert - 1) - kDelay], h);
   }
   __syncthreads();
   // phase 3

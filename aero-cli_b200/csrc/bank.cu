@@ -50,6 +50,9 @@ struct VfoRec {
   size_t out_bytes;  // payload bytes per block
   size_t out_off;    // offset of the payload row in the output buffers
   size_t taps_off[3];
+  std::vector<float> hil_nz;   // non-zero Hilbert taps ...
+  std::vector<int> hil_nz_idx; // ... and their indices
+  size_t hil_idx_off;
 };
 
 struct Group {   // VFOs sharing input stream and D: one launch of the main kernel per block
@@ -72,6 +75,7 @@ int ilcm(int a, int b) {
 struct aeroddc_bank {
   int fs = 0, B = 0, fmt = 0, device = 0;
   bool finalized = false;
+  int mode = AERODDC_MODE_EXACT;
   std::vector<VfoRec> vfos;
   std::vector<Group> groups;
   int vfo_pitch = 0;
@@ -86,6 +90,7 @@ struct aeroddc_bank {
   int* d_nco_len = nullptr;     // [vfo_pitch]
   int nck_max = 0;
   float* d_taps = nullptr;
+  int* d_hil_idx = nullptr;
   TailVfo* d_tail = nullptr;
   unsigned char* d_out = nullptr;
   size_t out_total = 0;
@@ -97,7 +102,9 @@ struct aeroddc_bank {
   unsigned char* h_in[2] = {nullptr, nullptr};
   unsigned char* h_out[3] = {nullptr, nullptr, nullptr};   // three slots: a payload stays valid until the next wait()
 
-  cudaStream_t s_compute = nullptr, s_copy = nullptr;
+  cudaStream_t s_compute = nullptr, s_copy = nullptr, s_d2h = nullptr;   // kernels | H2D of raw blocks | D2H of payloads
+  cudaEvent_t ev_tail[2] = {};   // payload rows of parity p written
+  cudaEvent_t ev_d2h[2] = {};    // payload rows of parity p copied out (may be overwritten)
   cudaEvent_t ev_h2d[2] = {};
   cudaEvent_t ev_sw0 = nullptr, ev_sw1 = nullptr;
   cudaEvent_t ev_done[3] = {}, ev_k0[3] = {}, ev_k1[3] = {}, ev_m0[3] = {}, ev_m1[3] = {};
@@ -114,38 +121,43 @@ struct aeroddc_bank {
 
 namespace {
 
-template <int NF, int FMT>
-cudaError_t launch_main_t(const MainParams& p, dim3 grid, cudaStream_t s) {
+template <int NF, int FMT, bool FAST>
+cudaError_t launch_main_m(const MainParams& p, dim3 grid, cudaStream_t s) {
   const int smem = TileSmem<FMT>::kTotal;
-  cudaError_t e = cudaFuncSetAttribute(ddc_main_kernel<NF, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(ddc_main_kernel<NF, FMT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  ddc_main_kernel<NF, FMT><<<grid, kThreads, smem, s>>>(p);
+  ddc_main_kernel<NF, FMT, FAST><<<grid, kThreads, smem, s>>>(p);
   return cudaGetLastError();
 }
+template <int NF, int FMT>
+cudaError_t launch_main_t(const MainParams& p, dim3 grid, cudaStream_t s, bool fast) {
+  return fast ? launch_main_m<NF, FMT, true>(p, grid, s) : launch_main_m<NF, FMT, false>(p, grid, s);
+}
 template <int FMT>
-cudaError_t launch_main_f(int nf, const MainParams& p, dim3 grid, cudaStream_t s) {
+cudaError_t launch_main_f(int nf, const MainParams& p, dim3 grid, cudaStream_t s, bool fast) {
   switch (nf) {
-    case 0: return launch_main_t<0, FMT>(p, grid, s);
-    case 1: return launch_main_t<1, FMT>(p, grid, s);
-    case 2: return launch_main_t<2, FMT>(p, grid, s);
-    case 3: return launch_main_t<3, FMT>(p, grid, s);
-    case 4: return launch_main_t<4, FMT>(p, grid, s);
-    default: return launch_main_t<5, FMT>(p, grid, s);
+    case 0: return launch_main_t<0, FMT>(p, grid, s, fast);
+    case 1: return launch_main_t<1, FMT>(p, grid, s, fast);
+    case 2: return launch_main_t<2, FMT>(p, grid, s, fast);
+    case 3: return launch_main_t<3, FMT>(p, grid, s, fast);
+    case 4: return launch_main_t<4, FMT>(p, grid, s, fast);
+    default: return launch_main_t<5, FMT>(p, grid, s, fast);
   }
 }
-cudaError_t launch_main(int fmt, int nf, const MainParams& p, dim3 grid, cudaStream_t s) {
-  if (fmt == AERODDC_CU8) return launch_main_f<FMT_CU8>(nf, p, grid, s);
-  if (fmt == AERODDC_CS16) return launch_main_f<FMT_CS16>(nf, p, grid, s);
-  return launch_main_f<FMT_CF32>(nf, p, grid, s);
+cudaError_t launch_main(int fmt, int nf, const MainParams& p, dim3 grid, cudaStream_t s, bool fast) {
+  if (fmt == AERODDC_CU8) return launch_main_f<FMT_CU8>(nf, p, grid, s, fast);
+  if (fmt == AERODDC_CS16) return launch_main_f<FMT_CS16>(nf, p, grid, s, fast);
+  return launch_main_f<FMT_CF32>(nf, p, grid, s, fast);
 }
 
 void free_all(aeroddc_bank* b) {
   cudaSetDevice(b->device);
   if (b->s_compute) cudaStreamSynchronize(b->s_compute);
   if (b->s_copy) cudaStreamSynchronize(b->s_copy);
+  if (b->s_d2h) cudaStreamSynchronize(b->s_d2h);
   cudaFree(b->d_rot); cudaFree(b->d_qlast); cudaFree(b->d_ckpt);
   cudaFree(b->d_state[0]); cudaFree(b->d_state[1]);
-  cudaFree(b->d_xd); cudaFree(b->d_xd_rows); cudaFree(b->d_nco_len); cudaFree(b->d_taps); cudaFree(b->d_tail); cudaFree(b->d_out);
+  cudaFree(b->d_xd); cudaFree(b->d_xd_rows); cudaFree(b->d_nco_len); cudaFree(b->d_taps); cudaFree(b->d_hil_idx); cudaFree(b->d_tail); cudaFree(b->d_out);
   cudaFree(b->d_in[0]); cudaFree(b->d_in[1]);
   for (int i = 0; i < 2; ++i) {
     if (b->h_in[i]) cudaFreeHost(b->h_in[i]);
@@ -163,6 +175,8 @@ void free_all(aeroddc_bank* b) {
   if (b->ev_sw1) cudaEventDestroy(b->ev_sw1);
   if (b->s_compute) cudaStreamDestroy(b->s_compute);
   if (b->s_copy) cudaStreamDestroy(b->s_copy);
+  if (b->s_d2h) cudaStreamDestroy(b->s_d2h);
+  for (int i = 0; i < 2; ++i) { if (b->ev_tail[i]) cudaEventDestroy(b->ev_tail[i]); if (b->ev_d2h[i]) cudaEventDestroy(b->ev_d2h[i]); }
 }
 
 // enqueue everything that follows the arrival of the raw block in device memory
@@ -195,26 +209,34 @@ int enqueue_block(aeroddc_bank* b, const void* dev_iq) {
     p.Wb = g.Wb;
     p.nco_len = g.fs_in;
     p.one = 1.0f;
+    p.transient = 4 * kNcoStride;
+    p.nck = b->nck_max;
     dim3 grid(g.nseg + 1, (g.count + kVfoPerCta - 1) / kVfoPerCta);
-    CU(launch_main(g.parent < 0 ? b->fmt : AERODDC_CF32, std::min(g.D, kFastStages), p, grid, s));
+    CU(launch_main(g.parent < 0 ? b->fmt : AERODDC_CF32, std::min(g.D, kFastStages), p, grid, s, b->mode == AERODDC_MODE_FAST));
     ++launches;
   }
   CU(cudaEventRecord(b->ev_m1[slot], s));
   {
+    // payload rows are double-buffered by block parity; wait until the copy-out of this parity (two blocks ago) is done
+    if (b->blocks_submitted >= 2) CU(cudaStreamWaitEvent(s, b->ev_d2h[par], 0));
     dim3 grid(b->tail_chunks, (unsigned)b->vfos.size());
-    tail_kernel<<<grid, kTailThreads, b->tail_smem, s>>>(b->d_tail);
+    tail_kernel<<<grid, kTailThreads, b->tail_smem, s>>>(b->d_tail, 1.0f, (size_t)par * b->out_total);
     CU(cudaGetLastError());
     ++launches;
   }
   CU(cudaEventRecord(b->ev_k1[slot], s));
-  // keep the last hist_max stage-D samples of every VFO in front of the next block
+  CU(cudaEventRecord(b->ev_tail[par], s));
+  // keep the last `hist` stage-D samples of every VFO in front of the next block
   if (b->any_hist) {
     xd_shift_kernel<<<(unsigned)b->vfos.size(), 256, 0, s>>>(b->d_tail);
     CU(cudaGetLastError());
     ++launches;
   }
-  CU(cudaMemcpyAsync(b->h_out[slot], b->d_out, b->out_total, cudaMemcpyDeviceToHost, s));
-  CU(cudaEventRecord(b->ev_done[slot], s));
+  // payloads leave on their own stream, overlapping the next block's kernels
+  CU(cudaStreamWaitEvent(b->s_d2h, b->ev_tail[par], 0));
+  CU(cudaMemcpyAsync(b->h_out[slot], b->d_out + (size_t)par * b->out_total, b->out_total, cudaMemcpyDeviceToHost, b->s_d2h));
+  CU(cudaEventRecord(b->ev_d2h[par], b->s_d2h));
+  CU(cudaEventRecord(b->ev_done[slot], b->s_d2h));
   b->launches_per_block = launches;
   b->blocks_submitted++;
   return AERODDC_OK;
@@ -268,6 +290,14 @@ int aeroddc_bank_create(aeroddc_bank** out, int sample_rate, int block_len, int 
   return AERODDC_OK;
 }
 
+int aeroddc_bank_set_mode(aeroddc_bank* b, int mode) {
+  if (!b) return fail(AERODDC_ERR_ARG, "NULL bank");
+  if (b->blocks_submitted > 0) return fail(AERODDC_ERR_STATE, "the arithmetic mode cannot change once blocks were processed");
+  if (mode != AERODDC_MODE_EXACT && mode != AERODDC_MODE_FAST) return fail(AERODDC_ERR_ARG, "unknown mode %d", mode);
+  b->mode = mode;
+  return AERODDC_OK;
+}
+
 int aeroddc_bank_add_vfo(aeroddc_bank* b, const aeroddc_vfo_desc* d) {
   if (!b || !d) return fail(AERODDC_ERR_ARG, "NULL argument");
   if (b->finalized) return fail(AERODDC_ERR_STATE, "bank already finalized");
@@ -301,7 +331,7 @@ int aeroddc_bank_add_vfo(aeroddc_bank* b, const aeroddc_vfo_desc* d) {
     return fail(AERODDC_ERR_DESIGN, "filter design rejected (fs=%d D=%d late=%d bw=%d)", r.fs_in, d->decim_count, late, d->filter_bw);
   if (r.plan.n_out < 1) return fail(AERODDC_ERR_ARG, "no output samples per block");
   const int T = (int)r.plan.late_taps.size(), U = (int)r.plan.usb_taps.size();
-  if (U > 4096) return fail(AERODDC_ERR_ARG, "fir_usb with %d taps is not supported (max 4096)", U);
+  if (U > (late > 0 ? 1024 : 4096)) return fail(AERODDC_ERR_ARG, "fir_usb with %d taps is not supported (max %d)", U, late > 0 ? 1024 : 4096);
   r.hist = d->demod_usb ? (U + kHilbert - 1) * std::max(late, 1) + T : 0;
   r.hist = (r.hist + 1) & ~1;
   r.out_bytes = d->demod_usb ? (size_t)r.plan.n_out * 2 : (d->compress_style == 1 ? (size_t)r.plan.n_out : (size_t)r.plan.n_out * 2);
@@ -385,14 +415,18 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
   }
 
   // ---- stage-D rows and payload rows ----
-  size_t taps_total = 0, out_off = 0, xd_total = 0;
+  size_t taps_total = 0, out_off = 0, xd_total = 0, idx_total = 0;
   for (VfoRec& r : b->vfos) {
     r.xd_off = xd_total;
     xd_total += ((size_t)r.hist + r.plan.n_stage + 1) & ~(size_t)1;
     if (r.hist > 0) b->any_hist = true;
     r.taps_off[0] = taps_total; taps_total += r.plan.late_taps.size();
     r.taps_off[1] = taps_total; taps_total += r.plan.usb_taps.size();
-    r.taps_off[2] = taps_total; taps_total += r.plan.hilbert_taps.size();
+    r.hil_nz.clear(); r.hil_nz_idx.clear();
+    for (size_t i = 0; i < r.plan.hilbert_taps.size(); ++i)
+      if (r.plan.hilbert_taps[i] != 0.0f) { r.hil_nz.push_back(r.plan.hilbert_taps[i]); r.hil_nz_idx.push_back((int)i); }
+    r.taps_off[2] = taps_total; taps_total += r.hil_nz.size();
+    r.hil_idx_off = idx_total; idx_total += r.hil_nz.size();
     r.out_off = out_off;
     if (r.children) r.out_bytes = 0;   // a main VFO with sub-VFOs only feeds them (vfo.cpp:167-172)
     out_off += (r.out_bytes + 15) & ~(size_t)15;
@@ -405,15 +439,19 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
   CU(dmalloc((void**)&b->d_xd_rows, sizeof(float2*) * b->vfo_pitch));
   CU(cudaMemcpy(b->d_xd_rows, h_rows.data(), sizeof(float2*) * b->vfo_pitch, cudaMemcpyHostToDevice));
   std::vector<float> h_taps(std::max<size_t>(taps_total, 1));
+  std::vector<int> h_idx(std::max<size_t>(idx_total, 1));
   for (const VfoRec& r : b->vfos) {
     std::copy(r.plan.late_taps.begin(), r.plan.late_taps.end(), h_taps.begin() + r.taps_off[0]);
     std::copy(r.plan.usb_taps.begin(), r.plan.usb_taps.end(), h_taps.begin() + r.taps_off[1]);
-    std::copy(r.plan.hilbert_taps.begin(), r.plan.hilbert_taps.end(), h_taps.begin() + r.taps_off[2]);
+    std::copy(r.hil_nz.begin(), r.hil_nz.end(), h_taps.begin() + r.taps_off[2]);
+    std::copy(r.hil_nz_idx.begin(), r.hil_nz_idx.end(), h_idx.begin() + r.hil_idx_off);
   }
+  CU(dmalloc((void**)&b->d_hil_idx, sizeof(int) * h_idx.size()));
+  CU(cudaMemcpy(b->d_hil_idx, h_idx.data(), sizeof(int) * h_idx.size(), cudaMemcpyHostToDevice));
   CU(dmalloc((void**)&b->d_taps, sizeof(float) * h_taps.size()));
   CU(cudaMemcpy(b->d_taps, h_taps.data(), sizeof(float) * h_taps.size(), cudaMemcpyHostToDevice));
-  CU(dmalloc((void**)&b->d_out, b->out_total));
-  CU(cudaMemset(b->d_out, 0, b->out_total));
+  CU(dmalloc((void**)&b->d_out, 2 * b->out_total));   // two parities: the tail of block k+1 runs while block k's payloads copy out
+  CU(cudaMemset(b->d_out, 0, 2 * b->out_total));
   std::vector<TailVfo> h_tail(nv);
   size_t tail_smem = 0;
   int max_out = 0;
@@ -425,6 +463,8 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
     t.late_taps = b->d_taps + r.taps_off[0];
     t.usb_taps = b->d_taps + r.taps_off[1];
     t.hil_taps = b->d_taps + r.taps_off[2];
+    t.hil_idx = b->d_hil_idx + r.hil_idx_off;
+    t.n_hil = (int)r.hil_nz.size();
     t.n_stage = r.plan.n_stage;
     t.n_out = r.children ? 0 : r.plan.n_out;
     t.hist = r.hist;
@@ -436,8 +476,9 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
     t.scalecomp = r.d.scale_comp;
     t.gain = r.d.gain;
     max_out = std::max(max_out, t.n_out);
-    const size_t sm = sizeof(float2) * (kHilbert - 1 + t.U + kTailChunk) + sizeof(float) * (t.U + kTailChunk) +
-                      sizeof(float) * (t.T + t.U + kHilbert) + 16;
+    const size_t n_m = kHilbert - 1 + t.U + kTailChunk;
+    const size_t sm = sizeof(float) * (2 * n_m + t.U + kTailChunk + t.T + t.U + 2 * kHilbert + 2) +
+                      (t.late > 0 ? sizeof(float2) * ((n_m - 1) * t.late + t.T) : 0) + 16;
     tail_smem = std::max(tail_smem, sm);
   }
   b->tail_smem = tail_smem;
@@ -464,6 +505,11 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
   CU(cudaEventCreate(&b->ev_sw1));
   CU(cudaStreamCreateWithFlags(&b->s_compute, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&b->s_copy, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&b->s_d2h, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CU(cudaEventCreateWithFlags(&b->ev_tail[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&b->ev_d2h[i], cudaEventDisableTiming));
+  }
 
   // ---- NCO checkpoints: the exact sequential recurrence, one thread per VFO ----
   {
@@ -593,6 +639,8 @@ int aeroddc_bank_stopwatch(aeroddc_bank* b, int which, float* ms) {
   if (which == 0) { CU(cudaEventRecord(b->ev_sw0, b->s_compute)); return AERODDC_OK; }
   if (which == 1) { CU(cudaEventRecord(b->ev_sw0, b->s_copy)); return AERODDC_OK; }
   if (which != 2 || !ms) return fail(AERODDC_ERR_ARG, "which must be 0, 1 or 2 (with ms)");
+  // the region ends when the last payload copy has finished: make the compute stream wait for it first
+  if (b->blocks_submitted > 0) CU(cudaStreamWaitEvent(b->s_compute, b->ev_d2h[(b->blocks_submitted - 1) & 1], 0));
   CU(cudaEventRecord(b->ev_sw1, b->s_compute));
   CU(cudaEventSynchronize(b->ev_sw1));
   CU(cudaEventElapsedTime(ms, b->ev_sw0, b->ev_sw1));

@@ -91,9 +91,40 @@ __device__ __forceinline__ P2 hb_out(const Ones& k, P2 e0, P2 e1, P2 e2, P2 e3, 
   P2 m0 = mul2s(s0, HB_P0), m2 = mul2s(s2, HB_P2), m4 = mul2s(s4, HB_P4), m5 = mul2s(o0, HB_P5);
   return add2(k, add2(k, add2(k, m0, m2), m4), m5);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Tolerance mode (AERODDC_MODE_FAST): the same chain with fused multiply-adds. It is NOT bit-identical
+// to the reference; it stays within BASELINE.json's tolerance (max |err| <= 1e-4 of full scale, error
+// SNR >= 80 dB on signals of normal level) at ~55 % of the exact mode's FP32 work:
+//  * oscillator: exact checkpoints every kNcoStride samples (the same table as the exact mode); in
+//    between, one fused complex rotation per sample (the recurrence's amplitude factor is 1 +- 1e-7 in
+//    steady state). The ~200-sample amplitude transient after each table restart and the restart
+//    itself run the full recurrence (fused).
+//  * mix and half-band taps: fma chains instead of separately rounded products.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void nco_rotate_fast(float& a, float& b, const Rot& rot) {
+  unpack2(fma2(rot.b, bcast2(b), mul2s(rot.a, a)), a, b);
+}
+__device__ __forceinline__ void nco_step_fused(float& a, float& b, const Rot& rot) {
+  const P2 n = fma2(rot.b, bcast2(b), mul2s(rot.a, a));
+  float nr, ni;
+  unpack2(n, nr, ni);
+  const float nm = 1.95f - fmaf(ni, ni, nr * nr);
+  unpack2(mul2s(n, nm), a, b);
+}
+__device__ __forceinline__ P2 mix_fast(float a, float b, const float2& s) {
+  return fma2(pack2(-s.y, s.x), bcast2(b), mul2s(pack2(s.x, s.y), a));
+}
+__device__ __forceinline__ P2 hb_out_fast(const Ones& k, P2 e0, P2 e1, P2 e2, P2 e3, P2 e4, P2 xe, P2 o0) {
+  const P2 s0 = add2(k, e0, xe), s2 = add2(k, e1, e4), s4 = add2(k, e2, e3);
+  return fma2(s4, bcast2(HB_P4), fma2(o0, bcast2(HB_P5), fma2(s2, bcast2(HB_P2), mul2s(s0, HB_P0))));
+}
+
 // consume the pair (x[2j], x[2j+1]) and return output j
+template <bool FAST>
 __device__ __forceinline__ P2 hb_pair(const Ones& k, HbState& h, P2 xe, P2 xo) {
-  const P2 y = hb_out(k, h.e[0], h.e[1], h.e[2], h.e[3], h.e[4], xe, h.o[0]);
+  const P2 y = FAST ? hb_out_fast(k, h.e[0], h.e[1], h.e[2], h.e[3], h.e[4], xe, h.o[0])
+                    : hb_out(k, h.e[0], h.e[1], h.e[2], h.e[3], h.e[4], xe, h.o[0]);
   h.e[0] = h.e[1]; h.e[1] = h.e[2]; h.e[2] = h.e[3]; h.e[3] = h.e[4]; h.e[4] = xe;
   h.o[0] = h.o[1]; h.o[1] = h.o[2]; h.o[2] = xo;
   return y;
@@ -118,6 +149,8 @@ struct MainParams {
   int Wb;                    // warm-up of the boundary role: 11*2^D (it needs 11 samples of history per stage)
   int nco_len;               // L = (int)Fs, the oscillator table length
   float one;                 // 1.0f (see add2)
+  int transient;             // tolerance mode: table indices below this use the full recurrence
+  int nck;                   // rows of ckpt
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -159,7 +192,7 @@ template <int FMT> __device__ __forceinline__ float2 load_raw(const void* base, 
 // restart from (1,0), oscillator.cpp:31-39) and absolute sample 0 (mixed with q[L-1], because the
 // constructor leaves _vector at the last table entry, oscillator.cpp:12-27).
 // ---------------------------------------------------------------------------------------------
-template <int NF, bool SPECIAL>
+template <int NF, bool SPECIAL, bool FAST>
 __device__ __forceinline__ void fast_chunk(const Ones& k1, float& oa, float& ob, const Rot& rot,
                                            HbState (&hb)[kFastStages > 0 ? kFastStages : 1],
                                            const float2* __restrict__ tile, P2 (&out)[kChunk >> NF],
@@ -171,17 +204,19 @@ __device__ __forceinline__ void fast_chunk(const Ones& k1, float& oa, float& ob,
     if (SPECIAL) {
       if (idx == nco_len) { idx = 0; oa = 1.0f; ob = 0.0f; }
     }
-    nco_step(k1, oa, ob, rot);
+    if (!FAST) nco_step(k1, oa, ob, rot);
+    else if (SPECIAL) nco_step_fused(oa, ob, rot);     // restart transient: full recurrence
+    else nco_rotate_fast(oa, ob, rot);
     float a = oa, b = ob;
     if (SPECIAL) { if (n_abs + i == 0) { a = qa; b = qb; } idx++; }
-    x0[i] = mix(k1, a, b, s);
+    x0[i] = FAST ? mix_fast(a, b, s) : mix(k1, a, b, s);
   }
   if (!SPECIAL) idx += kChunk;
   // NF half-band stages, compacting in place (output j overwrites slot j after slots 2j, 2j+1 were read)
 #pragma unroll
   for (int s = 0; s < NF; ++s) {
 #pragma unroll
-    for (int j = 0; j < (kChunk >> (s + 1)); ++j) x0[j] = hb_pair(k1, hb[s], x0[2 * j], x0[2 * j + 1]);
+    for (int j = 0; j < (kChunk >> (s + 1)); ++j) x0[j] = hb_pair<FAST>(k1, hb[s], x0[2 * j], x0[2 * j + 1]);
   }
 #pragma unroll
   for (int i = 0; i < (kChunk >> NF); ++i) out[i] = x0[i];
@@ -197,6 +232,7 @@ struct DeepSmem {
 };
 
 // push one sample into deep stage `ds`; returns true and the output in y when the sample was even-phase
+template <bool FAST>
 __device__ __forceinline__ bool deep_push(const Ones& k1, const DeepSmem& sm, int ds, bool odd, P2 x, P2& y) {
   if (odd) {   // store x[2j+1]
     sm.at(ds, 5) = sm.at(ds, 6);
@@ -205,7 +241,7 @@ __device__ __forceinline__ bool deep_push(const Ones& k1, const DeepSmem& sm, in
     return false;
   }
   const P2 e0 = sm.at(ds, 0), e1 = sm.at(ds, 1), e2 = sm.at(ds, 2), e3 = sm.at(ds, 3), e4 = sm.at(ds, 4), o0 = sm.at(ds, 5);
-  y = hb_out(k1, e0, e1, e2, e3, e4, x, o0);
+  y = FAST ? hb_out_fast(k1, e0, e1, e2, e3, e4, x, o0) : hb_out(k1, e0, e1, e2, e3, e4, x, o0);
   sm.at(ds, 0) = e1; sm.at(ds, 1) = e2; sm.at(ds, 2) = e3; sm.at(ds, 3) = e4; sm.at(ds, 4) = x;
   return true;
 }
@@ -224,7 +260,7 @@ __device__ __forceinline__ void store_p2(float2* p, P2 c) { float a, b; unpack2(
 // Straightforward per-thread code with local-memory rings; it runs on one extra CTA per VFO group
 // concurrently with the segment CTAs, so its speed does not matter.
 // ---------------------------------------------------------------------------------------------
-template <int FMT>
+template <int FMT, bool FAST>
 __device__ void boundary_role(const MainParams& p, int vfo, bool active) {
   P2 eh[kMaxStages][5];
   P2 oh[kMaxStages][6];
@@ -250,11 +286,14 @@ __device__ void boundary_role(const MainParams& p, int vfo, bool active) {
   for (int i = 0; i < p.Wb; ++i) {
     const float2 cd = load_raw<FMT>(p.iq, (size_t)start + i);
     if (idx == p.nco_len) { idx = 0; oa = 1.0f; ob = 0.0f; }
-    nco_step(k1, oa, ob, rot);
+    if (FAST && (idx % kNcoStride) == 0) { const float2 c = p.ckpt[(size_t)(idx / kNcoStride) * p.vfo_pitch + vfo]; oa = c.x; ob = c.y; }
+    if (!FAST) nco_step(k1, oa, ob, rot);
+    else if (idx < p.transient) nco_step_fused(oa, ob, rot);
+    else nco_rotate_fast(oa, ob, rot);
     float a = oa, b = ob;
     if (n0 + i == 0) { a = ql.x; b = ql.y; }
     idx++;
-    P2 x = mix(k1, a, b, cd);
+    P2 x = FAST ? mix_fast(a, b, cd) : mix(k1, a, b, cd);
     int cnt = i;
 #pragma unroll 1
     for (int s = 0; s < p.D; ++s) {
@@ -263,7 +302,8 @@ __device__ void boundary_role(const MainParams& p, int vfo, bool active) {
         oh[s][5] = x;
         break;
       }
-      const P2 y = hb_out(k1, eh[s][0], eh[s][1], eh[s][2], eh[s][3], eh[s][4], x, oh[s][3]);
+      const P2 y = FAST ? hb_out_fast(k1, eh[s][0], eh[s][1], eh[s][2], eh[s][3], eh[s][4], x, oh[s][3])
+                        : hb_out(k1, eh[s][0], eh[s][1], eh[s][2], eh[s][3], eh[s][4], x, oh[s][3]);
       for (int k = 0; k < 4; ++k) eh[s][k] = eh[s][k + 1];
       eh[s][4] = x;
       x = y;
@@ -293,7 +333,7 @@ template <int FMT> struct TileSmem {
   static constexpr int kTotal = kRawStages * kRawBytes + kCvtBytes + kDeepBytes + 64;
 };
 
-template <int NF, int FMT>
+template <int NF, int FMT, bool FAST>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const MainParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   using TS = TileSmem<FMT>;
@@ -308,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
   const int vfo = p.vfo_base + (active ? slot : 0);     // inactive threads shadow VFO 0 of the slice, never store
 
   if ((int)blockIdx.x == p.nseg) {
-    if (p.D > 0) boundary_role<FMT>(p, vfo, active);
+    if (p.D > 0) boundary_role<FMT, FAST>(p, vfo, active);
     return;
   }
 
@@ -384,6 +424,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
   const int out_first = seg_start >> p.D;                 // first stage-D index this segment owns
   int out_pos = first >> p.D;                             // stage-D index of the next output produced
   unsigned chunk_ctr = 0;                                 // chunks since `first` (first is 2^D aligned)
+  float2 nxt = make_float2(0.f, 0.f);                     // tolerance mode: prefetched checkpoint of stride nxt_k
+  int nxt_k = -1;
 
   for (int t = 0; t < ntiles; ++t) {
     const int n = min(kTile, total - t * kTile);
@@ -401,9 +443,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
 #pragma unroll 1
     for (int c = 0; c < n; c += kChunk) {
       P2 out[kChunk >> NF];
-      const bool special = (idx + kChunk > p.nco_len) || (n_abs == 0);
-      if (special) fast_chunk<NF, true>(k1, oa, ob, rot, hb, tile + c, out, idx, p.nco_len, n_abs, ql.x, ql.y);
-      else         fast_chunk<NF, false>(k1, oa, ob, rot, hb, tile + c, out, idx, p.nco_len, n_abs, ql.x, ql.y);
+      // rare variant: oscillator table wrap inside the chunk, absolute sample 0, and (tolerance mode) the restart transient
+      const bool special = (idx + kChunk > p.nco_len) || (n_abs == 0) || (FAST && idx < p.transient);
+      if (FAST && !special && (idx % kNcoStride) == 0) {   // tolerance mode: snap back to the exact table every stride
+        const int kk = idx / kNcoStride;
+        const float2 c0 = (kk == nxt_k) ? nxt : p.ckpt[(size_t)kk * p.vfo_pitch + vfo];
+        oa = c0.x; ob = c0.y;
+        nxt_k = min(kk + 1, p.nck - 1);                     // prefetch the next stride's checkpoint (used 8 chunks later)
+        nxt = p.ckpt[(size_t)nxt_k * p.vfo_pitch + vfo];
+      }
+      if (special) fast_chunk<NF, true, FAST>(k1, oa, ob, rot, hb, tile + c, out, idx, p.nco_len, n_abs, ql.x, ql.y);
+      else         fast_chunk<NF, false, FAST>(k1, oa, ob, rot, hb, tile + c, out, idx, p.nco_len, n_abs, ql.x, ql.y);
       n_abs += kChunk;
       if (NF < kFastStages) {
         // D == NF < kFastStages: every fast output is a stage-D sample
@@ -421,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
 #pragma unroll 1
         for (; s < ndeep; ++s) {
           P2 y;
-          if (!deep_push(k1, dsm, s, cc & 1u, x, y)) { produced = false; break; }
+          if (!deep_push<FAST>(k1, dsm, s, cc & 1u, x, y)) { produced = false; break; }
           x = y;
           cc >>= 1;
         }

@@ -9,6 +9,8 @@ bank = aeroddc.Bank(Fs,B,aeroddc.CF32,0)
 rng = np.random.default_rng(1)
 freqs = rng.integers(int(-0.45*Fs), int(0.45*Fs), nv)
 for i,f in enumerate(freqs): bank.add_vfo(float(f),D,L,0,0.05,1,1,1,"V%04d"%i)
+import os
+if os.environ.get("AERODDC_FAST"): bank.set_mode(aeroddc.MODE_FAST)
 bank.finalize()
 print('finalize %.2fs, dev MB %.1f'%(time.time()-t0, bank.device_bytes()/1e6))
 s0 = bank.host_slot(0); s1 = bank.host_slot(1)
