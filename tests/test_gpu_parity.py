@@ -281,3 +281,44 @@ def test_mode_cannot_change_after_first_block():
     with pytest.raises(a.AeroDdcError):
         bank.set_mode(a.MODE_EXACT)
     bank.close()
+
+
+@pytest.mark.parametrize("fs,blk,D,late", [(300000, 57600, 3, 0), (250000, 51200, 8, 5), (99968, 32000, 2, 0)])
+def test_oscillator_table_wrap_in_the_middle_of_a_block(fs, blk, D, late):
+    """The reference's table has (int)Fs entries; when Fs is not a multiple of the block length the
+    restart (and its amplitude transient) falls inside a block, inside a segment, inside a chunk."""
+    rng = np.random.default_rng(fs)
+    vfos = [dict(mixer=float(rng.integers(-fs // 3, fs // 3)), D=D, L=late, gain=0.4) for _ in range(3)]
+    bank = make_bank(fs, blk, FMT_CF32, vfos)
+    oracles = make_oracles(fs, blk, vfos)
+    nblocks = 2 * fs // blk + 3            # at least two restarts
+    for b in range(nblocks):
+        x = synth_raw(FMT_CF32, b * blk, blk, seed=3, amp=0.8)
+        bank.process(x)
+        for i, o in enumerate(oracles):
+            assert bank.output(i)[0] == o.process(x), (i, b)
+    bank.close()
+
+
+@pytest.mark.parametrize("fs,blk,D,late", [(300000, 57600, 3, 0), (250000, 51200, 8, 5)])
+def test_fast_mode_tolerance_across_table_restart(fs, blk, D, late):
+    a = _aeroddc()
+    rng = np.random.default_rng(fs + 1)
+    f = float(rng.integers(-fs // 3, fs // 3))
+    bank = a.Bank(fs, blk, a.CF32, 0)
+    bank.add_vfo(f, D, late, 0, 0.6, 1, 1, 1, "FWRAP")
+    bank.set_mode(a.MODE_FAST)
+    bank.finalize()
+    o = Oracle(fs, blk, D, late, f, 0.6, 0)
+    for b in range(2 * fs // blk + 3):
+        x = synth_raw(FMT_CF32, b * blk, blk, seed=4, amp=0.9)
+        bank.process(x)
+        sg = bank.stage_d(0, blk >> D).astype(np.float64)
+        so = o.stage(D).astype(np.float64) if o.process(x) is not None else None
+        if b > 0:
+            snr_f = 10 * np.log10((so * so).sum() / max(((sg - so) ** 2).sum(), 1e-300))
+            assert snr_f >= 95.0, (b, snr_f)
+        got = np.frombuffer(bank.output(0)[0], np.int16)
+        want = np.frombuffer(o._out.tobytes(), np.int16)
+        assert parity_metrics(got, want)[0] <= 1e-4
+    bank.close()
