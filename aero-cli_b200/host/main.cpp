@@ -6,6 +6,8 @@
 //   --anchors         drive stand-alone `vfo` objects over the SURVEY.md section-8c anchor inputs and print the hashes
 #include <cinttypes>
 #include <csignal>
+#include <ctime>
+#include <vector>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -69,8 +71,26 @@ int run_anchors() {
 }
 }  // namespace
 
+// publish a few known messages through the real socket path (libzmq via dlopen): wire-format self test, no GPU
+int run_zmq_selftest(const std::string& addr) {
+  ZmqPublisher pub;
+  pub.setAddress(addr);
+  pub.setBind(true);
+  pub.connect();
+  if (!pub.connected) { fprintf(stderr, "bind failed or libzmq not found\n"); return 1; }
+  std::vector<int16_t> payload(600);
+  for (int round = 0; round < 200; ++round) {   // PUB/SUB drops messages until the subscriber has joined: keep sending
+    for (int i = 0; i < 600; ++i) payload[i] = (int16_t)(i * 7 - 1000 + round);
+    pub.publish((unsigned char*)payload.data(), (uint32_t)(payload.size() * 2), "VFO42-long-topic", 48000);
+    pub.publish((unsigned char*)payload.data(), 0, "EMPTY", 12000);   // len 0: nothing is sent (zmqpublisher.cpp:67)
+    struct timespec ts = {0, 10 * 1000 * 1000};
+    nanosleep(&ts, nullptr);
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
-  std::string device, ini;
+  std::string device, ini, zmq_addr;
   bool biast = false, dcc = false, plan = false, hash = false, anchors = false;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
@@ -80,6 +100,7 @@ int main(int argc, char** argv) {
     else if (a == "--plan") plan = true;
     else if (a == "--hash") hash = true;
     else if (a == "--anchors") anchors = true;
+    else if (a == "--zmq-selftest" && i + 1 < argc) zmq_addr = argv[++i];
     else if (a == "-v" || a == "--verbose") {}
     else if (a == "-h" || a == "--help") {
       printf("usage: aero-publish-b200 -d <file=path,format=cu8|cs16|cf32[,repeat=N] | synthetic=seed[,format=..][,blocks=N]> [--enable-dcc] [--hash] <settings.ini>\n"
@@ -87,6 +108,7 @@ int main(int argc, char** argv) {
       return 0;
     } else ini = a;
   }
+  if (!zmq_addr.empty()) return run_zmq_selftest(zmq_addr);
   if (anchors) return run_anchors();
   if (ini.empty()) { fprintf(stderr, "settings file required\n"); return 2; }
   if (plan) {

@@ -127,6 +127,42 @@ def test_settings_errors(tmp_path):
     assert subprocess.run([BIN, "--plan", str(tmp_path / "missing.ini")], capture_output=True).returncode == 1
 
 
+def test_zmq_wire_format_over_a_real_socket():
+    """ZmqPublisher through libzmq (dlopen) to a pyzmq SUB socket: three frames - 5 topic bytes, uint32 LE
+    rate, payload - as aero-decode's consumer expects (zmqpublisher.cpp:61-73, decode/decode.cpp:283-366)."""
+    zmq = pytest.importorskip("zmq")
+    _build()
+    import glob
+    import socket
+    import struct
+
+    libs = glob.glob(os.path.join(os.path.dirname(zmq.__file__), "..", "pyzmq.libs", "libzmq*.so*"))
+    if not libs:
+        pytest.skip("no bundled libzmq to dlopen")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    env = dict(os.environ, AERODDC_LIBZMQ=os.path.abspath(libs[0]))
+    proc = subprocess.Popen([BIN, "--zmq-selftest", "tcp://127.0.0.1:%d" % port], env=env)
+    try:
+        ctx = zmq.Context.instance()
+        sub = ctx.socket(zmq.SUB)
+        sub.setsockopt(zmq.SUBSCRIBE, b"VFO42")
+        sub.setsockopt(zmq.RCVTIMEO, 5000)
+        sub.connect("tcp://127.0.0.1:%d" % port)
+        frames = sub.recv_multipart()
+        assert len(frames) == 3
+        assert frames[0] == b"VFO42"                       # exactly the first five bytes of the topic
+        assert struct.unpack("<I", frames[1])[0] == 48000
+        p = np.frombuffer(frames[2], np.int16)
+        assert p.size == 600 and np.array_equal(np.diff(p), np.full(599, 7, np.int16))
+        sub.close(0)
+    finally:
+        proc.kill()
+        proc.wait()
+
+
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 def test_standalone_vfo_objects_reproduce_survey_anchors():
