@@ -3,6 +3,7 @@
 // Extras for replay and testing:
 //   --plan            parse the settings only (no device, no GPU) and print the VFO tree as JSON
 //   --hash            capture every ZeroMQ message in-process and print per-topic FNV-1a-64 / bytes as JSON
+//   --dump DIR        additionally write every topic's payloads to DIR/<topic>.i16 (+ .meta) for tools/replay_payloads.py
 //   --anchors         drive stand-alone `vfo` objects over the SURVEY.md section-8c anchor inputs and print the hashes
 #include <cinttypes>
 #include <csignal>
@@ -21,8 +22,19 @@ void on_signal(int) { if (g_pub) g_pub->handleInterrupt(); }
 
 struct TopicAcc { uint64_t fnv = 1469598103934665603ull; uint64_t bytes = 0; uint32_t rate = 0; uint64_t msgs = 0; };
 std::map<std::string, TopicAcc> g_acc;
+std::string g_dump_dir;
+std::map<std::string, FILE*> g_dump;
 void sink(const std::string& topic5, uint32_t rate, const unsigned char* p, uint32_t n) {
   TopicAcc& a = g_acc[std::string(topic5.c_str())];
+  if (!g_dump_dir.empty()) {   // DIR/<topic>.i16 + DIR/<topic>.meta ("rate bytes_per_message"), read by tools/replay_payloads.py
+    const std::string t(topic5.c_str());
+    FILE*& f = g_dump[t];
+    if (!f) {
+      f = fopen((g_dump_dir + "/" + t + ".i16").c_str(), "wb");
+      if (FILE* m = fopen((g_dump_dir + "/" + t + ".meta").c_str(), "w")) { fprintf(m, "%u %u\n", rate, n); fclose(m); }
+    }
+    if (f) fwrite(p, 1, n, f);
+  }
   for (uint32_t i = 0; i < n; ++i) a.fnv = (a.fnv ^ p[i]) * 1099511628211ull;
   a.bytes += n; a.rate = rate; a.msgs++;
 }
@@ -99,6 +111,7 @@ int main(int argc, char** argv) {
     else if (a == "--enable-dcc") dcc = true;
     else if (a == "--plan") plan = true;
     else if (a == "--hash") hash = true;
+    else if (a == "--dump" && i + 1 < argc) { g_dump_dir = argv[++i]; hash = true; }
     else if (a == "--anchors") anchors = true;
     else if (a == "--zmq-selftest" && i + 1 < argc) zmq_addr = argv[++i];
     else if (a == "-v" || a == "--verbose") {}
@@ -138,6 +151,7 @@ int main(int argc, char** argv) {
   pub.run();
   pub.wait();
   fprintf(stderr, "processed %lld blocks of %d samples\n", pub.blocksProcessed(), pub.blockLen());
+  for (auto& kv : g_dump) if (kv.second) fclose(kv.second);
   if (hash) print_acc();
   return pub.lastError().empty() ? 0 : 1;
 }
