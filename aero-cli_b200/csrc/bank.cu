@@ -60,6 +60,9 @@ struct Group {   // VFOs sharing input stream and D: one launch of the main kern
   int D, base, count;
   int fs_in, blk_in;
   int S, W, Wb, nseg;
+  int Q, P;          // parts per segment and part length (chained CTAs, see ddc_kernels.cuh)
+  int* d_flags = nullptr;
+  float2* d_hand = nullptr;
 };
 
 int raw_bytes(int fmt) { return fmt == AERODDC_CU8 ? 2 : (fmt == AERODDC_CS16 ? 4 : 8); }
@@ -88,6 +91,7 @@ struct aeroddc_bank {
   float2* d_xd = nullptr;       // all stage-D rows, per VFO: [hist][n_stage]
   float2** d_xd_rows = nullptr; // [vfo_pitch] pointer to stage-D index 0 of each column's row
   int* d_nco_len = nullptr;     // [vfo_pitch]
+  int* d_err = nullptr;         // chained-CTA watchdog flag
   int nck_max = 0;
   float* d_taps = nullptr;
   int* d_hil_idx = nullptr;
@@ -157,6 +161,8 @@ void free_all(aeroddc_bank* b) {
   if (b->s_d2h) cudaStreamSynchronize(b->s_d2h);
   cudaFree(b->d_rot); cudaFree(b->d_qlast); cudaFree(b->d_ckpt);
   cudaFree(b->d_state[0]); cudaFree(b->d_state[1]);
+  for (Group& g : b->groups) { cudaFree(g.d_flags); cudaFree(g.d_hand); }
+  cudaFree(b->d_err);
   cudaFree(b->d_xd); cudaFree(b->d_xd_rows); cudaFree(b->d_nco_len); cudaFree(b->d_taps); cudaFree(b->d_hil_idx); cudaFree(b->d_tail); cudaFree(b->d_out);
   cudaFree(b->d_in[0]); cudaFree(b->d_in[1]);
   for (int i = 0; i < 2; ++i) {
@@ -211,7 +217,14 @@ int enqueue_block(aeroddc_bank* b, const void* dev_iq) {
     p.one = 1.0f;
     p.transient = 4 * kNcoStride;
     p.nck = b->nck_max;
-    dim3 grid(g.nseg + 1, (g.count + kVfoPerCta - 1) / kVfoPerCta);
+    p.Q = g.Q;
+    p.P = g.P;
+    p.ngroups = (g.count + kVfoPerCta - 1) / kVfoPerCta;
+    p.epoch = (int)((b->blocks_submitted + 1) & 0x00FFFFFF);
+    p.flags = g.d_flags;
+    p.hand = g.d_hand;
+    p.err = b->d_err;
+    dim3 grid((unsigned)(p.ngroups * (1 + g.Q * g.nseg)));
     CU(launch_main(g.parent < 0 ? b->fmt : AERODDC_CF32, std::min(g.D, kFastStages), p, grid, s, b->mode == AERODDC_MODE_FAST));
     ++launches;
   }
@@ -375,19 +388,33 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
     g.W = g.D == 0 ? 0 : ((10 << g.D) + cstep - 1) / cstep * cstep;
     g.Wb = g.D == 0 ? 0 : (11 << g.D);
     const int nblk_y = (g.count + kVfoPerCta - 1) / kVfoPerCta;
-    // One wave of CTAs (kCtasPerSm per SM) is the minimum. The warp scheduler favours some resident warps, so the
-    // CTAs of a single wave finish at different times and the SMs idle at the end; more, shorter segments even
-    // that out at the price of one warm-up (W samples) each. Use up to 4 waves while warm-up stays under ~5 %.
-    const int one_wave = std::max(1, (int)std::floor((double)kCtasPerSm * b->n_sm / nblk_y) - 1);   // -1: the boundary CTA
-    double w = waves;
-    if (!env_waves && g.W > 0) w = std::min(4.0, std::max(1.0, std::floor((double)g.blk_in / one_wave / (20.0 * g.W))));
-    const int target = std::max(1, (int)std::floor((double)kCtasPerSm * b->n_sm * w / nblk_y) - 1);
+    // One wave of CTAs (kCtasPerSm per SM) cuts the block into segments, each paying one warm-up of W samples.
+    // The warp scheduler favours some resident warps, so equal CTAs of a single wave finish at different times;
+    // each segment is therefore processed as Q chained parts by Q short CTAs (state handed over through HBM),
+    // which evens the load without further warm-ups. AERODDC_WAVES / AERODDC_PARTS override.
+    const int target = std::max(1, (int)std::floor((double)kCtasPerSm * b->n_sm * waves / nblk_y) - 1);   // -1: the boundary CTA
     int S = (g.blk_in + target - 1) / target;
     S = std::max(S, std::max(4 * g.W, 4096));
     S = (S + align - 1) / align * align;
     g.S = S;
     g.nseg = (g.blk_in + S - 1) / S;
+    const char* env_parts = getenv("AERODDC_PARTS");
+    int Q = env_parts ? std::max(1, atoi(env_parts)) : 16;
+    const int pal = ilcm(kTile, 1 << g.D);
+    while (Q > 1 && S / Q < 8 * pal) --Q;              // keep parts long enough that the hand-over stays negligible
+    Q = std::min(Q, 60);
+    g.Q = Q;
+    g.P = ((S + Q - 1) / Q + pal - 1) / pal * pal;
   }
+
+  for (Group& g : b->groups) {
+    const size_t nk = (size_t)((g.count + kVfoPerCta - 1) / kVfoPerCta) * g.nseg;
+    CU(cudaMalloc((void**)&g.d_flags, sizeof(int) * nk));
+    CU(cudaMemset(g.d_flags, 0, sizeof(int) * nk));
+    CU(cudaMalloc((void**)&g.d_hand, sizeof(float2) * nk * kHandSlots * kThreads));
+  }
+  CU(cudaMalloc((void**)&b->d_err, sizeof(int)));
+  CU(cudaMemset(b->d_err, 0, sizeof(int)));
 
   // ---- constant tables ----
   std::vector<float2> h_rot(b->vfo_pitch, make_float2(1.0f, 0.0f));
@@ -567,6 +594,10 @@ int aeroddc_bank_wait(aeroddc_bank* b) {
   b->last_launches = b->launches_per_block;
   b->cur_out = slot;
   b->blocks_done++;
+  int err = 0;
+  CU(cudaMemcpyAsync(&err, b->d_err, sizeof err, cudaMemcpyDeviceToHost, b->s_d2h));
+  CU(cudaStreamSynchronize(b->s_d2h));
+  if (err) return fail(AERODDC_ERR_CUDA, "a chained segment CTA timed out waiting for its predecessor (internal error)");
   return AERODDC_OK;
 }
 

@@ -29,6 +29,7 @@ constexpr int kMaxStages = 8;          // hdecimator[8], vfo.h:63
 constexpr int kFastStages = 5;         // half-band stages kept in registers
 constexpr int kStateSlots = 8;         // per stage: 5 even-phase + 3 odd-phase history samples
 constexpr int kNcoStride = 256;        // NCO checkpoint spacing (samples)
+constexpr int kHandSlots = kMaxStages * kStateSlots + 1;   // half-band history of every stage + oscillator state
 constexpr int kCtasPerSm = 4;          // 16 resident warps per SM at <= 128 registers per thread
 
 enum { FMT_CU8 = 0, FMT_CS16 = 1, FMT_CF32 = 2 };
@@ -151,6 +152,13 @@ struct MainParams {
   float one;                 // 1.0f (see add2)
   int transient;             // tolerance mode: table indices below this use the full recurrence
   int nck;                   // rows of ckpt
+  // A segment is processed as Q consecutive parts of P samples by Q different CTAs chained through HBM:
+  // CTA (q, k) waits for flag[k] == epoch*64 + q, loads the state CTA (q-1, k) left in `hand`, and passes it on.
+  int Q, P, ngroups;
+  int epoch;                 // unique per launch
+  int* flags;                // [ngroups][nseg]
+  float2* hand;              // [ngroups][nseg][kHandSlots][kThreads]
+  int* err;                  // set to 1 if a chained CTA gave up waiting (should never happen)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -321,7 +329,7 @@ __device__ void boundary_role(const MainParams& p, int vfo, bool active) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Main kernel. grid = (nseg + 1, vfo groups). blockIdx.x < nseg: segment role; == nseg: boundary.
+// Main kernel. 1-D grid: ngroups boundary CTAs, then Q * nseg * ngroups segment-part CTAs.
 // Shared memory: raw tile ring (TMA bulk copies) | converted float tiles (c, d), double-buffered |
 // deep-stage history | mbarriers.
 // ---------------------------------------------------------------------------------------------
@@ -343,22 +351,39 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TS::kRawStages * TS::kRawBytes + TS::kCvtBytes + TS::kDeepBytes);
 
   const int tid = threadIdx.x;
-  const int slot = blockIdx.y * kVfoPerCta + tid;       // this thread's VFO within the slice
+  // 1-D grid, dispatched in index order: [boundary CTA of every VFO group] then part 0 of every (group, segment),
+  // then part 1 of every (group, segment), ... so a CTA's predecessor in its chain always has a smaller index.
+  int bid = blockIdx.x;
+  const bool is_boundary = bid < p.ngroups;
+  int q = 0, gy = bid, seg = 0;
+  if (!is_boundary) {
+    bid -= p.ngroups;
+    const int per_q = p.nseg * p.ngroups;
+    q = bid / per_q;
+    const int rem = bid - q * per_q;
+    gy = rem / p.nseg;
+    seg = rem - gy * p.nseg;
+  }
+  const int slot = gy * kVfoPerCta + tid;               // this thread's VFO within the slice
   const bool active = slot < p.vfo_count;
   const int vfo = p.vfo_base + (active ? slot : 0);     // inactive threads shadow VFO 0 of the slice, never store
 
-  if ((int)blockIdx.x == p.nseg) {
+  if (is_boundary) {
     if (p.D > 0) boundary_role<FMT, FAST>(p, vfo, active);
     return;
   }
 
-  const int seg = blockIdx.x;
   const int seg_start = seg * p.S;
-  const int seg_len = min(p.S, p.B - seg_start);
-  const int warm = seg == 0 ? 0 : p.W;                    // segment 0 starts from the saved history
-  const int first = seg_start - warm;                     // in-block index of the first sample processed
-  const int total = warm + seg_len;                       // multiple of max(kChunk, 2^D)
+  const int seg_end = min(seg_start + p.S, p.B);
+  const int part_start = seg_start + q * p.P;
+  const int part_end = min(part_start + p.P, seg_end);
+  const bool empty = part_start >= seg_end;               // short last segment: nothing left for this part
+  const int warm = (q > 0 || seg == 0) ? 0 : p.W;         // part 0 of segment 0 starts from the saved block history
+  const int first = part_start - warm;                    // in-block index of the first sample processed
+  const int total = empty ? 0 : warm + (part_end - part_start);   // multiple of max(kChunk, 2^D)
   const int ntiles = (total + kTile - 1) / kTile;
+  int* flag = p.flags + gy * p.nseg + seg;
+  float2* hand = p.hand + ((size_t)(gy * p.nseg + seg) * kHandSlots) * kThreads + tid;
 
   if (tid == 0) {
     for (int i = 0; i < TS::kRawStages; ++i) mbar_init(&bars[i], 1);
@@ -385,7 +410,28 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
   HbState hb[kFastStages > 0 ? kFastStages : 1];
   DeepSmem dsm; dsm.base = deep + tid;
   const int ndeep = p.D > NF ? p.D - NF : 0;
-  if (seg == 0) {
+  if (q > 0) {
+    // wait for the previous part of this segment, then take over its state
+    if (tid == 0) {
+      const int want = p.epoch * 64 + q;
+      int seen, spins = 0;
+      do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        if (seen != want) { __nanosleep(200); if (++spins > (1 << 24)) { *p.err = 1; break; } }
+      } while (seen != want);
+    }
+    __syncthreads();
+    __threadfence();
+#pragma unroll
+    for (int s = 0; s < NF; ++s) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) hb[s].e[k] = load_p2(hand + (size_t)(s * kStateSlots + k) * kThreads);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) hb[s].o[k] = load_p2(hand + (size_t)(s * kStateSlots + 5 + k) * kThreads);
+    }
+    for (int s = 0; s < ndeep; ++s)
+      for (int k = 0; k < kStateSlots; ++k) dsm.at(s, k) = load_p2(hand + (size_t)((NF + s) * kStateSlots + k) * kThreads);
+  } else if (seg == 0) {
 #pragma unroll
     for (int s = 0; s < NF; ++s) {
       const float2* st = p.state_in + (size_t)s * kStateSlots * p.vfo_pitch + vfo;
@@ -418,10 +464,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
     oa = c.x; ob = c.y;
     for (int i = 0; i < rem; ++i) nco_step(k1, oa, ob, rot);
   }
+  if (q > 0) {   // the oscillator continues exactly where the previous part stopped
+    const float2 o = hand[(size_t)(kHandSlots - 1) * kThreads];
+    oa = o.x; ob = o.y;
+  }
 
   // stage-D output cursor: outputs before the segment start (warm-up) are discarded
   float2* xd = p.xd_rows[vfo];
-  const int out_first = seg_start >> p.D;                 // first stage-D index this segment owns
+  const int out_first = part_start >> p.D;                // first stage-D index this part owns
   int out_pos = first >> p.D;                             // stage-D index of the next output produced
   unsigned chunk_ctr = 0;                                 // chunks since `first` (first is 2^D aligned)
   float2 nxt = make_float2(0.f, 0.f);                     // tolerance mode: prefetched checkpoint of stride nxt_k
@@ -481,6 +531,28 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
         }
         chunk_ctr++;
       }
+    }
+  }
+
+  // hand the state to the next part of this segment
+  if (q + 1 < p.Q) {
+    if (!empty || q == 0) {
+#pragma unroll
+      for (int s = 0; s < NF; ++s) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) store_p2(hand + (size_t)(s * kStateSlots + k) * kThreads, hb[s].e[k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) store_p2(hand + (size_t)(s * kStateSlots + 5 + k) * kThreads, hb[s].o[k]);
+      }
+      for (int s = 0; s < ndeep; ++s)
+        for (int k = 0; k < kStateSlots; ++k) store_p2(hand + (size_t)((NF + s) * kStateSlots + k) * kThreads, dsm.at(s, k));
+      hand[(size_t)(kHandSlots - 1) * kThreads] = make_float2(oa, ob);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const int done = p.epoch * 64 + q + 1;
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(done) : "memory");
     }
   }
 }

@@ -177,7 +177,7 @@ def test_block_contract_and_state_errors():
 
 def test_vfo_independence_and_segmentation_invariance(monkeypatch):
     """A VFO's bytes do not depend on which other VFOs share the bank, on its column, or on how the
-    block is cut into time segments (warm-up + boundary-state logic)."""
+    block is cut into time segments and chained parts (warm-up, boundary-state and state hand-over logic)."""
     fs, blk = 1536000, 384000
     rng = np.random.default_rng(17)
     vfos = _mixed_bank(fs, 140, rng, [5, 6, 7, 5])   # > 128: two VFO groups per segment
@@ -189,8 +189,9 @@ def test_vfo_independence_and_segmentation_invariance(monkeypatch):
         for i in (0, 1, 63, 127, 128, 139):
             ref.setdefault(i, []).append(big.output(i)[0])
     big.close()
-    for waves in ("0.25", "3"):
+    for waves, parts in (("0.25", "1"), ("3", "5"), ("1", "60")):
         monkeypatch.setenv("AERODDC_WAVES", waves)
+        monkeypatch.setenv("AERODDC_PARTS", parts)
         small = make_bank(fs, blk, FMT_CF32, [vfos[i] for i in (139, 0, 128)])
         for k, x in enumerate(xs):
             small.process(x)
