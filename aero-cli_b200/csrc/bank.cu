@@ -91,7 +91,8 @@ struct aeroddc_bank {
   float2* d_xd = nullptr;       // all stage-D rows, per VFO: [hist][n_stage]
   float2** d_xd_rows = nullptr; // [vfo_pitch] pointer to stage-D index 0 of each column's row
   int* d_nco_len = nullptr;     // [vfo_pitch]
-  int* d_err = nullptr;         // chained-CTA watchdog flag
+  int* d_err = nullptr;         // chained-CTA watchdog flag: device view of h_err (zero-copy pinned host memory)
+  volatile int* h_err = nullptr;
   int nck_max = 0;
   float* d_taps = nullptr;
   int* d_hil_idx = nullptr;
@@ -162,7 +163,7 @@ void free_all(aeroddc_bank* b) {
   cudaFree(b->d_rot); cudaFree(b->d_qlast); cudaFree(b->d_ckpt);
   cudaFree(b->d_state[0]); cudaFree(b->d_state[1]);
   for (Group& g : b->groups) { cudaFree(g.d_flags); cudaFree(g.d_hand); }
-  cudaFree(b->d_err);
+  if (b->h_err) cudaFreeHost((void*)b->h_err);
   cudaFree(b->d_xd); cudaFree(b->d_xd_rows); cudaFree(b->d_nco_len); cudaFree(b->d_taps); cudaFree(b->d_hil_idx); cudaFree(b->d_tail); cudaFree(b->d_out);
   cudaFree(b->d_in[0]); cudaFree(b->d_in[1]);
   for (int i = 0; i < 2; ++i) {
@@ -413,8 +414,9 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
     CU(cudaMemset(g.d_flags, 0, sizeof(int) * nk));
     CU(cudaMalloc((void**)&g.d_hand, sizeof(float2) * nk * kHandSlots * kThreads));
   }
-  CU(cudaMalloc((void**)&b->d_err, sizeof(int)));
-  CU(cudaMemset(b->d_err, 0, sizeof(int)));
+  CU(cudaHostAlloc((void**)&b->h_err, sizeof(int), cudaHostAllocMapped));
+  *b->h_err = 0;
+  CU(cudaHostGetDevicePointer((void**)&b->d_err, (void*)b->h_err, 0));
 
   // ---- constant tables ----
   std::vector<float2> h_rot(b->vfo_pitch, make_float2(1.0f, 0.0f));
@@ -594,10 +596,7 @@ int aeroddc_bank_wait(aeroddc_bank* b) {
   b->last_launches = b->launches_per_block;
   b->cur_out = slot;
   b->blocks_done++;
-  int err = 0;
-  CU(cudaMemcpyAsync(&err, b->d_err, sizeof err, cudaMemcpyDeviceToHost, b->s_d2h));
-  CU(cudaStreamSynchronize(b->s_d2h));
-  if (err) return fail(AERODDC_ERR_CUDA, "a chained segment CTA timed out waiting for its predecessor (internal error)");
+  if (*b->h_err) return fail(AERODDC_ERR_CUDA, "a chained segment CTA timed out waiting for its predecessor (internal error)");
   return AERODDC_OK;
 }
 
