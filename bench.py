@@ -242,7 +242,7 @@ def main():
     if rank == 0:
         host[0][:] = synth_block(1)
         host[1][:] = synth_block(2)
-    dbuf = [torch.empty(2 * BLOCK, dtype=torch.float32, device=dev) for _ in range(2)]
+    dbuf = [torch.empty(2 * BLOCK, dtype=torch.float32, device=dev) for _ in range(2)]   # grown to 4 for N > 1 below
     src = [torch.empty(2 * BLOCK, dtype=torch.float32, device=dev) for _ in range(2)] if (world > 1 and rank == 0) else None
     if rank == 0:
         for i in range(2):
@@ -255,55 +255,59 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def feed_device(k):
-        """Make block k available in this rank's HBM and hand it to the bank (async)."""
-        b = k & 1
-        ev = None
-        if world > 1:
-            if rank == 0:
-                dbuf[b].copy_(src[b], non_blocking=True)   # stays in HBM; keeps the source blocks intact
-            dist.broadcast(dbuf[b], src=0)
-            e = torch.cuda.Event()
-            e.record()
-            ev = e.cuda_event
-            feed_device.keep.append(e)
-            if len(feed_device.keep) > 4:
-                feed_device.keep.pop(0)
-        bank.submit_device(dbuf[b].data_ptr(), ev)
+    # N > 1: the raw block travels rank 0 -> all ranks by NCCL broadcast TWO blocks ahead of its use (four device
+    # buffers), so the collective's kernel runs while the previous block's CTAs drain instead of between two blocks.
+    nbuf = 4 if world > 1 else 2
+    while len(dbuf) < nbuf:
+        dbuf.append(torch.empty(2 * BLOCK, dtype=torch.float32, device=dev))
+    events = [None] * nbuf
 
-    feed_device.keep = []
-
-    def run_device(n):
-        inflight = 0
-        for k in range(n):
-            if inflight == 2:
-                bank.wait(); inflight -= 1
-            feed_device(k); inflight += 1
-        while inflight:
-            bank.wait(); inflight -= 1
-
-    def run_e2e(n):
-        """Host-facing path: pinned host block -> H2D -> kernels -> D2H, pipelined two deep.
-        N > 1: rank 0 uploads, NCCL broadcasts, every rank downloads its payloads."""
-        inflight = 0
-        for k in range(n):
-            if inflight == 2:
-                bank.wait(); inflight -= 1
-            b = k & 1
-            if world == 1:
-                bank.submit(host[b])
+    def prefetch(k, from_host):
+        """Start moving block k into this rank's HBM buffer k % nbuf (async)."""
+        if world == 1:
+            return
+        b = k % nbuf
+        if rank == 0:
+            if from_host:
+                dbuf[b].copy_(torch.from_numpy(host[k & 1]), non_blocking=True)    # H2D from the pinned ring
             else:
-                if rank == 0:
-                    dbuf[b].copy_(torch.from_numpy(host[b]), non_blocking=True)
-                dist.broadcast(dbuf[b], src=0)
-                e = torch.cuda.Event(); e.record()
-                feed_device.keep.append(e)
-                if len(feed_device.keep) > 4:
-                    feed_device.keep.pop(0)
-                bank.submit_device(dbuf[b].data_ptr(), e.cuda_event)
+                dbuf[b].copy_(src[k & 1], non_blocking=True)                        # stays in HBM
+        dist.broadcast(dbuf[b], src=0)
+        e = torch.cuda.Event()
+        e.record()
+        events[b] = e
+
+    def run_blocks(n, from_host, on_wait=None):
+        """n blocks, two in flight. from_host: the host-facing path (pinned host blocks, H2D inside)."""
+        for k in range(min(2, n)):
+            prefetch(k, from_host)
+        inflight = 0
+        for k in range(n):
+            if inflight == 2:
+                bank.wait(); inflight -= 1
+                if on_wait:
+                    on_wait()
+            if world == 1:
+                if from_host:
+                    bank.submit(host[k & 1])
+                else:
+                    bank.submit_device(dbuf[k & 1].data_ptr(), None)
+            else:
+                b = k % nbuf
+                bank.submit_device(dbuf[b].data_ptr(), events[b].cuda_event)
+                if k + 2 < n:
+                    prefetch(k + 2, from_host)       # buffer (k+2) % 4 was last read by block k-2, which has completed
             inflight += 1
         while inflight:
             bank.wait(); inflight -= 1
+            if on_wait:
+                on_wait()
+
+    def run_device(n):
+        run_blocks(n, False)
+
+    def run_e2e(n):
+        run_blocks(n, True)
 
     peak_tflops, probe_clock = aeroddc.measure_fp32_peak(local_rank)
 
@@ -316,15 +320,7 @@ def main():
     main_ms = []
     bank.stopwatch_start(False)
     t0 = time.perf_counter()
-    inflight = 0
-    for k in range(args.steps):
-        if inflight == 2:
-            bank.wait(); inflight -= 1
-            main_ms.append(bank.last_main_ms())
-        feed_device(k); inflight += 1
-    while inflight:
-        bank.wait(); inflight -= 1
-        main_ms.append(bank.last_main_ms())
+    run_blocks(args.steps, False, on_wait=lambda: main_ms.append(bank.last_main_ms()))
     dev_ms = bank.stopwatch_stop()
     sync_all()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -352,15 +348,7 @@ def main():
         sync_all()
         fast_main = []
         bank.stopwatch_start(False)
-        inflight = 0
-        for k in range(args.steps):
-            if inflight == 2:
-                bank.wait(); inflight -= 1
-                fast_main.append(bank.last_main_ms())
-            feed_device(k); inflight += 1
-        while inflight:
-            bank.wait(); inflight -= 1
-            fast_main.append(bank.last_main_ms())
+        run_blocks(args.steps, False, on_wait=lambda: fast_main.append(bank.last_main_ms()))
         fast_ms = bank.stopwatch_stop()
         sync_all()
         fbank.close()
