@@ -323,3 +323,58 @@ def test_fast_mode_tolerance_across_table_restart(fs, blk, D, late):
         want = np.frombuffer(o._out.tobytes(), np.int16)
         assert parity_metrics(got, want)[0] <= 1e-4
     bank.close()
+
+
+@pytest.mark.parametrize("fs,blk,D,late,bw", [
+    (20480, 5120, 8, 0, 0),        # 20 stage-D samples per block: the 124-sample history spans six blocks
+    (40960, 10240, 8, 5, 0),       # 40 stage-D samples, 8 outputs per block, 669 samples of history
+    (1536000, 384000, 5, 0, 1500), # 309-tap fir_usb
+    (288000, 72000, 0, 6, 1500),   # D = 0 (no half-band stage at all) with late /6 and fir_usb
+])
+def test_small_blocks_and_long_filters_vs_oracle(fs, blk, D, late, bw):
+    rng = np.random.default_rng(blk + D)
+    vfos = [dict(mixer=float(rng.integers(-fs // 3, fs // 3)), D=D, L=late, bw=bw, gain=0.45) for _ in range(2)]
+    bank = make_bank(fs, blk, FMT_CF32, vfos)
+    oracles = make_oracles(fs, blk, vfos)
+    for b in range(12 if blk < 20000 else 4):
+        x = synth_raw(FMT_CF32, b * blk, blk, seed=8, amp=0.9)
+        bank.process(x)
+        for i, o in enumerate(oracles):
+            assert bank.output(i)[0] == o.process(x), (i, b)
+    bank.close()
+
+
+def test_int16_overflow_wraps_like_the_reference_build():
+    """usb*gain*32768 beyond int16: undefined in C++, but the reference's x86 build truncates to int32 and keeps the
+    low 16 bits; oracle and GPU pin that behaviour (float->short)."""
+    fs, blk = 288000, 57600
+    vfos = [dict(mixer=12345.0, D=2, L=0, gain=40.0), dict(mixer=-3000.0, D=1, L=6, gain=1e6)]
+    bank = make_bank(fs, blk, FMT_CF32, vfos)
+    oracles = make_oracles(fs, blk, vfos)
+    wrapped = 0
+    for b in range(3):
+        x = synth_anchor(b * blk, blk)
+        bank.process(x)
+        for i, o in enumerate(oracles):
+            want = o.process(x)
+            assert bank.output(i)[0] == want
+        wrapped += int(np.abs(np.diff(np.frombuffer(want, np.int16).astype(np.int32))).max() > 30000)
+    assert wrapped > 0      # the test signal really overflowed
+    bank.close()
+
+
+def test_many_vfos_three_decimations_two_formats():
+    """300 VFOs in three D-groups (3 + 1 + 1 CTAs wide), cs16 input, against the oracle on a sample of columns."""
+    fs, blk = 1536000, 384000
+    rng = np.random.default_rng(300)
+    vfos = _mixed_bank(fs, 300, rng, [7] * 150 + [6] * 100 + [5] * 50)
+    bank = make_bank(fs, blk, FMT_CS16, vfos)
+    picks = [0, 127, 128, 149, 150, 249, 250, 299]
+    oracles = make_oracles(fs, blk, [vfos[i] for i in picks])
+    for b in range(3):
+        raw = synth_raw(FMT_CS16, b * blk, blk, seed=12, amp=0.7)
+        x = unpack(FMT_CS16, raw)
+        bank.process(raw)
+        for j, i in enumerate(picks):
+            assert bank.output(i)[0] == oracles[j].process(x), (i, b)
+    bank.close()

@@ -98,3 +98,16 @@ def test_components_vs_reference():
         r0 = np.zeros(4, np.float32)
         R.ref_nco(fs, f, 0, 2, r0.ctypes.data)
         assert np.array_equal(r0[:2], q[-2:]) and np.array_equal(r0[2:], q[2:4])   # sample 0 uses q[L-1]
+
+
+@needs_ref
+def test_oracle_int16_overflow_matches_reference_build():
+    """Out-of-range float->short is undefined in C++; the oracle pins what the reference's x86 build does."""
+    fs, blk = 288000, 57600
+    from oracle_bind import synth_anchor
+    for (f, D, L, gain) in [(12345.0, 2, 0, 40.0), (-3000.0, 1, 6, 1e6)]:
+        o = Oracle(fs, blk, D, L, f, gain, 0)
+        r = RefVfo(fs, blk, D, L, f, gain, 0)
+        for b in range(3):
+            x = synth_anchor(b * blk, blk)
+            assert o.process(x) == r.process(x)[r.topic][1]
