@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
     if (tid == 0 && t + TS::kRawStages < ntiles) issue(t + TS::kRawStages);   // raw slot is free again
     const float2* tile = dst;
 
-#pragma unroll 1
+#pragma unroll 2
     for (int c = 0; c < n; c += kChunk) {
       P2 out[kChunk >> NF];
       // rare variant: oscillator table wrap inside the chunk, absolute sample 0, and (tolerance mode) the restart transient
