@@ -55,6 +55,7 @@ struct TailVfo {
   const float* hil_taps;   // the non-zero Hilbert taps, in ascending tap order ...
   const int* hil_idx;      // ... and their tap indices (every other tap of the 125 is exactly +-0.0f and cannot change a sum)
   int n_hil;
+  int hil_regular;         // 1 when the non-zero taps are exactly the odd indices 1, 3, ..., 2*n_hil-1 (always, for the 125-tap design)
   int n_stage, n_out;
   int hist;              // stage-D samples kept in front of the block
   int late, T, U;
@@ -163,8 +164,13 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(const TailVfo* __res
   for (int j = tid; j < n_u; j += kTailThreads) {
     float h = 0.0f;
     const float* w = mQ + j;
+    if (v.hil_regular) {
+#pragma unroll 31
+      for (int i = 0; i < v.n_hil; ++i) h = __fadd_rn(h, __fmul_rn(th[i], w[2 * i + 1]));
+    } else {
 #pragma unroll 7
-    for (int i = 0; i < v.n_hil; ++i) h = __fadd_rn(h, __fmul_rn(th[i], w[thi[i]]));
+      for (int i = 0; i < v.n_hil; ++i) h = __fadd_rn(h, __fmul_rn(th[i], w[thi[i]]));
+    }
     u[j] = __fsub_rn(mI[j + (kHilbert - 1) - kDelay], h);
   }
   __syncthreads();

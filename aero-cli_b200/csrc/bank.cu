@@ -494,6 +494,8 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
     t.hil_taps = b->d_taps + r.taps_off[2];
     t.hil_idx = b->d_hil_idx + r.hil_idx_off;
     t.n_hil = (int)r.hil_nz.size();
+    t.hil_regular = 1;
+    for (size_t j = 0; j < r.hil_nz_idx.size(); ++j) if (r.hil_nz_idx[j] != (int)(2 * j + 1)) t.hil_regular = 0;
     t.n_stage = r.plan.n_stage;
     t.n_out = r.children ? 0 : r.plan.n_out;
     t.hist = r.hist;
