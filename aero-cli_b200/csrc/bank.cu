@@ -221,10 +221,10 @@ int enqueue_block(aeroddc_bank* b, const void* dev_iq) {
     p.Q = g.Q;
     p.P = g.P;
     p.ngroups = (g.count + kVfoPerCta - 1) / kVfoPerCta;
-    p.epoch = (int)((b->blocks_submitted + 1) & 0x00FFFFFF);
     p.flags = g.d_flags;
     p.hand = g.d_hand;
     p.err = b->d_err;
+    if (g.Q > 1) CU(cudaMemsetAsync(g.d_flags, 0, sizeof(int) * (size_t)p.ngroups * g.nseg, s));
     dim3 grid((unsigned)(p.ngroups * (1 + g.Q * g.nseg)));
     CU(launch_main(g.parent < 0 ? b->fmt : AERODDC_CF32, std::min(g.D, kFastStages), p, grid, s, b->mode == AERODDC_MODE_FAST));
     ++launches;

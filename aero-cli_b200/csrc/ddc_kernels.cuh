@@ -153,10 +153,9 @@ struct MainParams {
   int transient;             // tolerance mode: table indices below this use the full recurrence
   int nck;                   // rows of ckpt
   // A segment is processed as Q consecutive parts of P samples by Q different CTAs chained through HBM:
-  // CTA (q, k) waits for flag[k] == epoch*64 + q, loads the state CTA (q-1, k) left in `hand`, and passes it on.
+  // CTA (q, k) waits for flag[k] == q, loads the state CTA (q-1, k) left in `hand`, and passes it on (flag = q+1).
   int Q, P, ngroups;
-  int epoch;                 // unique per launch
-  int* flags;                // [ngroups][nseg]
+  int* flags;                // [ngroups][nseg] parts completed; zeroed by the host before every launch
   float2* hand;              // [ngroups][nseg][kHandSlots][kThreads]
   int* err;                  // set to 1 if a chained CTA gave up waiting (should never happen)
 };
@@ -413,7 +412,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
   if (q > 0) {
     // wait for the previous part of this segment, then take over its state
     if (tid == 0) {
-      const int want = p.epoch * 64 + q;
+      const int want = q;
       int seen, spins = 0;
       do {
         asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
@@ -551,7 +550,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-      const int done = p.epoch * 64 + q + 1;
+      const int done = q + 1;
       asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(done) : "memory");
     }
   }
