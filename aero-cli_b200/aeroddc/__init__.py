@@ -45,6 +45,9 @@ ABI_SYMBOLS = [
     "aeroddc_bank_last_timing", "aeroddc_bank_last_main_ms", "aeroddc_bank_device_bytes",
     "aeroddc_bank_destroy", "aeroddc_last_error", "aeroddc_measure_fp32_peak", "aeroddc_abi_version",
     "aeroddc_design_lowpass", "aeroddc_design_hilbert", "aeroddc_design_rotation", "aeroddc_bank_stopwatch", "aeroddc_bank_set_mode",
+    "aeroddc_fleet_create", "aeroddc_fleet_add_vfo", "aeroddc_fleet_set_mode", "aeroddc_fleet_finalize", "aeroddc_fleet_host_slot",
+    "aeroddc_fleet_submit", "aeroddc_fleet_wait", "aeroddc_fleet_process", "aeroddc_fleet_output", "aeroddc_fleet_num_devices",
+    "aeroddc_fleet_device_of", "aeroddc_fleet_destroy",
 ]
 
 _lib = None
@@ -77,6 +80,19 @@ def lib():
         L.aeroddc_bank_device_bytes.argtypes = [vp, ctypes.POINTER(cz)]
         L.aeroddc_bank_stopwatch.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_float)]
         L.aeroddc_bank_set_mode.argtypes = [vp, ci]
+        L.aeroddc_fleet_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ctypes.POINTER(ci), ci]
+        L.aeroddc_fleet_add_vfo.argtypes = [vp, ctypes.POINTER(VfoDesc)]
+        L.aeroddc_fleet_set_mode.argtypes = [vp, ci]
+        L.aeroddc_fleet_finalize.argtypes = [vp]
+        L.aeroddc_fleet_host_slot.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(cz)]
+        L.aeroddc_fleet_submit.argtypes = [vp, vp, cz]
+        L.aeroddc_fleet_wait.argtypes = [vp]
+        L.aeroddc_fleet_process.argtypes = [vp, vp, cz]
+        L.aeroddc_fleet_output.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(cz), ctypes.POINTER(ctypes.c_uint32)]
+        L.aeroddc_fleet_num_devices.argtypes = [vp]
+        L.aeroddc_fleet_device_of.argtypes = [vp, ci]
+        L.aeroddc_fleet_destroy.argtypes = [vp]
+        L.aeroddc_fleet_destroy.restype = None
         L.aeroddc_bank_destroy.argtypes = [vp]
         L.aeroddc_bank_destroy.restype = None
         L.aeroddc_last_error.restype = ctypes.c_char_p
@@ -216,6 +232,74 @@ class Bank:
     def close(self):
         if self._h:
             self._L.aeroddc_bank_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Fleet:
+    """One bank per GPU of the node behind one handle (include/aeroddc.h, aeroddc_fleet_*): VFOs sharded over
+    the devices, raw blocks uploaded once and broadcast with NCCL. Same call order as Bank."""
+
+    def __init__(self, sample_rate, block_len, in_format=CF32, devices=(0,)):
+        self._L = lib()
+        self._h = ctypes.c_void_p()
+        self.block_len, self.in_format = block_len, in_format
+        devs = (ctypes.c_int * len(devices))(*devices)
+        _check(self._L.aeroddc_fleet_create(ctypes.byref(self._h), sample_rate, block_len, in_format, devs, len(devices)))
+
+    def add_vfo(self, mixer_freq, decim_count, late_decimate=0, filter_bw=0, gain=0.01, demod_usb=1,
+                compress_style=1, scale_comp=1, topic="", parent=-1):
+        d = VfoDesc(float(mixer_freq), int(decim_count), int(late_decimate), int(filter_bw), float(gain),
+                    int(demod_usb), int(compress_style), int(scale_comp), topic.encode()[:63], int(parent))
+        return _check(self._L.aeroddc_fleet_add_vfo(self._h, ctypes.byref(d)))
+
+    def set_mode(self, mode):
+        _check(self._L.aeroddc_fleet_set_mode(self._h, mode))
+
+    def finalize(self):
+        _check(self._L.aeroddc_fleet_finalize(self._h))
+
+    def _ptr(self, block):
+        if isinstance(block, np.ndarray):
+            if block.dtype != _NP_DTYPE[self.in_format] or not block.flags.c_contiguous or block.size != 2 * self.block_len:
+                raise AeroDdcError("block must be a C-contiguous %s array of %d values" % (_NP_DTYPE[self.in_format].__name__, 2 * self.block_len))
+            return block.ctypes.data
+        return int(block)
+
+    def process(self, block):
+        _check(self._L.aeroddc_fleet_process(self._h, self._ptr(block), self.block_len))
+
+    def submit(self, block):
+        _check(self._L.aeroddc_fleet_submit(self._h, self._ptr(block), self.block_len))
+
+    def wait(self):
+        _check(self._L.aeroddc_fleet_wait(self._h))
+
+    def host_slot(self, slot):
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        _check(self._L.aeroddc_fleet_host_slot(self._h, slot, ctypes.byref(p), ctypes.byref(n)))
+        return np.frombuffer((ctypes.c_ubyte * n.value).from_address(p.value), dtype=np.dtype(_NP_DTYPE[self.in_format]))
+
+    def output(self, vfo):
+        p, n, r = ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_uint32()
+        _check(self._L.aeroddc_fleet_output(self._h, vfo, ctypes.byref(p), ctypes.byref(n), ctypes.byref(r)))
+        return ctypes.string_at(p.value, n.value), r.value
+
+    @property
+    def num_devices(self):
+        return self._L.aeroddc_fleet_num_devices(self._h)
+
+    def device_of(self, vfo):
+        return self._L.aeroddc_fleet_device_of(self._h, vfo)
+
+    def close(self):
+        if self._h:
+            self._L.aeroddc_fleet_destroy(self._h)
             self._h = ctypes.c_void_p()
 
     def __del__(self):

@@ -31,6 +31,18 @@ int fail(int code, const char* fmt, ...) {
   t_err = buf;
   return code;
 }
+}  // namespace
+// shared with fleet.cu
+int aeroddc_set_error(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  t_err = buf;
+  return code;
+}
+namespace {
 #define CU(x)                                                                                            \
   do {                                                                                                   \
     cudaError_t e_ = (x);                                                                                \

@@ -1,5 +1,6 @@
 #include "publisher.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -28,7 +29,14 @@ Publisher::Publisher(const std::string& deviceStr, bool enableBiast_, bool enabl
   try {
     // DC correction needs float samples on the host, so the bank then ingests cf32
     const int fmt = enableDcc ? AERODDC_CF32 : source->format();
-    bank = std::make_shared<aero::DdcBank>(Fs, buflen / 2, fmt, 0);
+    // GPUs: "gpus=N" in the device string (or AERODDC_GPUS) shards the VFOs over devices 0..N-1 (NCCL broadcast of each block)
+    int ngpu = 1;
+    const size_t gp = deviceStr.find("gpus=");
+    if (gp != std::string::npos) ngpu = atoi(deviceStr.c_str() + gp + 5);
+    else if (const char* e = getenv("AERODDC_GPUS")) ngpu = atoi(e);
+    std::vector<int> devs;
+    for (int i = 0; i < std::max(1, ngpu); ++i) devs.push_back(i);
+    bank = std::make_shared<aero::DdcBank>(Fs, buflen / 2, fmt, devs);
     for (vfo* m : VFOmain) m->addToBank(bank, -1);
     for (vfo* f : VFOflat) f->addToBank(bank, -1);
     bank->finalize();
@@ -187,7 +195,7 @@ void Publisher::readerThread() {
   std::vector<unsigned char> raw;
   if (!running) goto Exit;
   for (int i = 0; i < 2; ++i)
-    if (aeroddc_bank_host_slot(bank->handle(), i, &slot[i], &bytes) != AERODDC_OK) { error = aeroddc_last_error(); goto Exit; }
+    if (aeroddc_fleet_host_slot(bank->handle(), i, &slot[i], &bytes) != AERODDC_OK) { error = aeroddc_last_error(); goto Exit; }
   if (enableDcc) raw.resize((size_t)(buflen / 2) * aero::formatBytes(source->format()));
   while (running) {
     void* dst = slot[blocks & 1];   // the source writes straight into the pinned ring

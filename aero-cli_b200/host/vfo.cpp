@@ -6,19 +6,19 @@
 
 namespace aero {
 
-DdcBank::DdcBank(int sample_rate, int block_len, int in_format, int device) : block_len_(block_len), format_(in_format) {
-  if (aeroddc_bank_create(&bank_, sample_rate, block_len, in_format, device) != AERODDC_OK)
-    throw std::runtime_error(std::string("aeroddc_bank_create: ") + aeroddc_last_error());
+DdcBank::DdcBank(int sample_rate, int block_len, int in_format, const std::vector<int>& devices) : block_len_(block_len), format_(in_format) {
+  if (aeroddc_fleet_create(&bank_, sample_rate, block_len, in_format, devices.data(), (int)devices.size()) != AERODDC_OK)
+    throw std::runtime_error(std::string("aeroddc_fleet_create: ") + aeroddc_last_error());
 }
-DdcBank::~DdcBank() { aeroddc_bank_destroy(bank_); }
+DdcBank::~DdcBank() { aeroddc_fleet_destroy(bank_); }
 void DdcBank::finalize() {
   if (finalized_) return;
-  if (aeroddc_bank_finalize(bank_) != AERODDC_OK) throw std::runtime_error(std::string("aeroddc_bank_finalize: ") + aeroddc_last_error());
+  if (aeroddc_fleet_finalize(bank_) != AERODDC_OK) throw std::runtime_error(std::string("aeroddc_fleet_finalize: ") + aeroddc_last_error());
   finalized_ = true;
 }
 void DdcBank::process(const void* host_iq, size_t n_complex) {
-  if (aeroddc_bank_process(bank_, host_iq, n_complex) != AERODDC_OK)
-    throw std::runtime_error(std::string("aeroddc_bank_process: ") + aeroddc_last_error());
+  if (aeroddc_fleet_process(bank_, host_iq, n_complex) != AERODDC_OK)
+    throw std::runtime_error(std::string("aeroddc_fleet_process: ") + aeroddc_last_error());
 }
 
 }  // namespace aero
@@ -100,8 +100,8 @@ void vfo::addToBank(const std::shared_ptr<aero::DdcBank>& bank, int parent) {
   d.scale_comp = scalecomp;
   strncpy(d.topic, zmqTopic.c_str(), sizeof d.topic - 1);
   d.parent = parent;
-  const int idx = aeroddc_bank_add_vfo(bank->handle(), &d);
-  if (idx < 0) throw std::runtime_error(std::string("aeroddc_bank_add_vfo(") + zmqTopic + "): " + aeroddc_last_error());
+  const int idx = aeroddc_fleet_add_vfo(bank->handle(), &d);
+  if (idx < 0) throw std::runtime_error(std::string("aeroddc_fleet_add_vfo(") + zmqTopic + "): " + aeroddc_last_error());
   bank_ = bank;
   index_ = idx;
   if (mpVFOs)
@@ -110,7 +110,7 @@ void vfo::addToBank(const std::shared_ptr<aero::DdcBank>& bank, int parent) {
 
 void vfo::process(const std::vector<cpx_typef>& samples) {
   if (!bank_) {   // driven on its own, like the reference's object: private bank with this VFO and its sub-VFOs
-    auto bank = std::make_shared<aero::DdcBank>(Fs, samplesPerBuffer_, AERODDC_CF32, 0);
+    auto bank = std::make_shared<aero::DdcBank>(Fs, samplesPerBuffer_, AERODDC_CF32);
     addToBank(bank, -1);
     bank->finalize();
   }
@@ -128,8 +128,8 @@ void vfo::transmitData() {
   const void* payload = nullptr;
   size_t n = 0;
   uint32_t rate = 0;
-  if (aeroddc_bank_output(bank_->handle(), index_, &payload, &n, &rate) != AERODDC_OK)
-    throw std::runtime_error(std::string("aeroddc_bank_output: ") + aeroddc_last_error());
+  if (aeroddc_fleet_output(bank_->handle(), index_, &payload, &n, &rate) != AERODDC_OK)
+    throw std::runtime_error(std::string("aeroddc_fleet_output: ") + aeroddc_last_error());
   if (!demodUSB && zmqTopic.empty()) return;   // vfo.cpp:300: IQ is only sent when a topic is set
   ZmqPublisher& pub = zmqBind ? vfo::bind_publisher : connect_publisher;
   pub.publish((unsigned char*)payload, (uint32_t)n, zmqTopic, rate);

@@ -23,21 +23,22 @@
 typedef std::complex<float> cpx_typef;
 
 namespace aero {
-// RAII holder of one aeroddc_bank; shared by the VFOs that were batched into it.
+// RAII holder of one aeroddc_fleet (one GPU bank per device; a single device is the common case); shared by
+// the VFOs that were batched into it.
 class DdcBank {
  public:
-  DdcBank(int sample_rate, int block_len, int in_format, int device);
+  DdcBank(int sample_rate, int block_len, int in_format, const std::vector<int>& devices = {0});
   ~DdcBank();
   DdcBank(const DdcBank&) = delete;
   DdcBank& operator=(const DdcBank&) = delete;
-  aeroddc_bank* handle() const { return bank_; }
+  aeroddc_fleet* handle() const { return bank_; }
   int blockLen() const { return block_len_; }
   int format() const { return format_; }
   bool finalized() const { return finalized_; }
   void finalize();                                  // throws std::runtime_error with aeroddc_last_error()
   void process(const void* host_iq, size_t n_complex);
  private:
-  aeroddc_bank* bank_ = nullptr;
+  aeroddc_fleet* bank_ = nullptr;
   int block_len_, format_;
   bool finalized_ = false;
 };

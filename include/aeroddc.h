@@ -149,6 +149,31 @@ const char *aeroddc_last_error(void);
  * denominator SURVEY.md section 8d asks to measure in the same run): TFLOP/s counting FMA = 2. */
 int aeroddc_measure_fp32_peak(int device, double *tflops, double *sm_clock_mhz);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fleet: one bank per GPU of a node, driven from ONE host thread.
+ * VFOs are sharded over the devices (flat VFO i -> device i mod N; a main VFO takes its sub-VFOs with it),
+ * every raw block is uploaded once to devices[0] and broadcast to the others with NCCL (ncclBroadcast over
+ * NVLink; libnccl.so.2 is loaded at run time), each GPU runs its VFO subset and returns its own payloads.
+ * Same call order and error conventions as the bank; VFO indices are global (order of add_vfo).
+ * Replaces, like the bank, Publisher::demodData -> vfo::process for every VFO (publisher.cpp:285-306).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct aeroddc_fleet aeroddc_fleet;
+int aeroddc_fleet_create(aeroddc_fleet **out, int sample_rate, int block_len, int in_format, const int *devices, int n_devices);
+int aeroddc_fleet_add_vfo(aeroddc_fleet *fleet, const aeroddc_vfo_desc *desc);   /* desc->parent is a global index */
+int aeroddc_fleet_set_mode(aeroddc_fleet *fleet, int mode);
+int aeroddc_fleet_finalize(aeroddc_fleet *fleet);
+/* Pinned host slot 0/1 of the ingest GPU's ring (fill it directly to avoid a host copy). */
+int aeroddc_fleet_host_slot(aeroddc_fleet *fleet, int slot, void **ptr, size_t *bytes);
+/* submit: H2D to devices[0] + NCCL broadcast + every GPU's kernels and payload D2H, asynchronously (at most two
+ * blocks in flight); wait: the oldest submitted block's payloads are in host memory on every GPU. */
+int aeroddc_fleet_submit(aeroddc_fleet *fleet, const void *host_iq, size_t n_complex);
+int aeroddc_fleet_wait(aeroddc_fleet *fleet);
+int aeroddc_fleet_process(aeroddc_fleet *fleet, const void *host_iq, size_t n_complex);
+int aeroddc_fleet_output(aeroddc_fleet *fleet, int vfo, const void **payload, size_t *nbytes, uint32_t *rate);
+int aeroddc_fleet_num_devices(aeroddc_fleet *fleet);
+int aeroddc_fleet_device_of(aeroddc_fleet *fleet, int vfo);   /* index into the devices[] given at create */
+void aeroddc_fleet_destroy(aeroddc_fleet *fleet);
+
 /* Host-side coefficient designers, exposed so that callers and tests can inspect exactly the taps
  * the bank uploads. Pure CPU code (no device needed), bit-identical to firfilter::low_pass with the
  * Hamming window (firfilter.cpp:46-99,186-193), FIRHilbert::FIRHilbert (dsp.cpp:181-215) and the

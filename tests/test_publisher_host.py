@@ -211,3 +211,24 @@ def test_publisher_from_iq_file_matches_oracle_per_topic(tmp_path, ini, fmt, blo
         assert got[t]["bytes"] == len(acc[p["topic"]]) and got[t]["rate"] == o.out_rate and got[t]["messages"] == blocks
         assert got[t]["fnv1a64"] == "%016x" % fnv1a64(acc[p["topic"]]), t
     assert len(got) == len(leaves)
+
+
+@pytest.mark.gpu
+def test_publisher_on_two_gpus_matches_one_gpu(tmp_path):
+    """`gpus=2` in the device string: VFO subtrees sharded over two GPUs, NCCL broadcast; same bytes per topic."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _build()
+    path = os.path.join(DATA, "two_mains_1920k.ini")
+    head, _ = expected_plan(path)
+    B = head["block"]
+    f = tmp_path / "iq.bin"
+    with open(f, "wb") as fh:
+        for b in range(5):
+            fh.write(synth_raw(FMT_CU8, b * B, B, seed=17, amp=0.8).tobytes())
+    one = json.loads(subprocess.run([BIN, "-d", "file=%s,format=cu8" % f, "--hash", path], check=True, capture_output=True, text=True).stdout)
+    out = subprocess.run([BIN, "-d", "file=%s,format=cu8,gpus=2" % f, "--hash", path], check=True, capture_output=True, text=True).stdout
+    two = json.loads(out.strip().splitlines()[-1])      # NCCL may print its version banner on stdout first
+    assert one == two and len(one) == 5
