@@ -47,7 +47,7 @@ ABI_SYMBOLS = [
     "aeroddc_design_lowpass", "aeroddc_design_hilbert", "aeroddc_design_rotation", "aeroddc_bank_stopwatch", "aeroddc_bank_set_mode",
     "aeroddc_fleet_create", "aeroddc_fleet_add_vfo", "aeroddc_fleet_set_mode", "aeroddc_fleet_finalize", "aeroddc_fleet_host_slot",
     "aeroddc_fleet_submit", "aeroddc_fleet_wait", "aeroddc_fleet_process", "aeroddc_fleet_output", "aeroddc_fleet_num_devices",
-    "aeroddc_fleet_device_of", "aeroddc_fleet_destroy",
+    "aeroddc_fleet_device_of", "aeroddc_fleet_destroy", "aeroddc_bank_set_dc_correction", "aeroddc_fleet_set_dc_correction",
 ]
 
 _lib = None
@@ -80,6 +80,8 @@ def lib():
         L.aeroddc_bank_device_bytes.argtypes = [vp, ctypes.POINTER(cz)]
         L.aeroddc_bank_stopwatch.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_float)]
         L.aeroddc_bank_set_mode.argtypes = [vp, ci]
+        L.aeroddc_bank_set_dc_correction.argtypes = [vp, ci]
+        L.aeroddc_fleet_set_dc_correction.argtypes = [vp, ci]
         L.aeroddc_fleet_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ctypes.POINTER(ci), ci]
         L.aeroddc_fleet_add_vfo.argtypes = [vp, ctypes.POINTER(VfoDesc)]
         L.aeroddc_fleet_set_mode.argtypes = [vp, ci]
@@ -155,6 +157,9 @@ class Bank:
 
     def set_mode(self, mode):
         _check(self._L.aeroddc_bank_set_mode(self._h, mode))
+
+    def set_dc_correction(self, enable=True):
+        _check(self._L.aeroddc_bank_set_dc_correction(self._h, 1 if enable else 0))
 
     def finalize(self):
         _check(self._L.aeroddc_bank_finalize(self._h))

@@ -91,6 +91,9 @@ struct aeroddc_bank {
   int fs = 0, B = 0, fmt = 0, device = 0;
   bool finalized = false;
   int mode = AERODDC_MODE_EXACT;
+  bool dcc = false;
+  float* d_dcc_out = nullptr;    // DC-corrected cf32 block
+  float* d_dcc_state = nullptr;  // running average per rail
   std::vector<VfoRec> vfos;
   std::vector<Group> groups;
   int vfo_pitch = 0;
@@ -176,6 +179,7 @@ void free_all(aeroddc_bank* b) {
   cudaFree(b->d_state[0]); cudaFree(b->d_state[1]);
   for (Group& g : b->groups) { cudaFree(g.d_flags); cudaFree(g.d_hand); }
   if (b->h_err) cudaFreeHost((void*)b->h_err);
+  cudaFree(b->d_dcc_out); cudaFree(b->d_dcc_state);
   cudaFree(b->d_xd); cudaFree(b->d_xd_rows); cudaFree(b->d_nco_len); cudaFree(b->d_taps); cudaFree(b->d_hil_idx); cudaFree(b->d_tail); cudaFree(b->d_out);
   cudaFree(b->d_in[0]); cudaFree(b->d_in[1]);
   for (int i = 0; i < 2; ++i) {
@@ -205,6 +209,14 @@ int enqueue_block(aeroddc_bank* b, const void* dev_iq) {
   const int par = (int)(b->blocks_submitted & 1);
   int launches = 0;
   CU(cudaEventRecord(b->ev_k0[slot], s));
+  if (b->dcc) {   // sequential DC removal of the raw stream; the VFOs then read the corrected cf32 block
+    if (b->fmt == AERODDC_CU8) dcc_kernel<0><<<1, 32, 0, s>>>(dev_iq, b->d_dcc_out, b->d_dcc_state, b->B);
+    else if (b->fmt == AERODDC_CS16) dcc_kernel<1><<<1, 32, 0, s>>>(dev_iq, b->d_dcc_out, b->d_dcc_state, b->B);
+    else dcc_kernel<2><<<1, 32, 0, s>>>(dev_iq, b->d_dcc_out, b->d_dcc_state, b->B);
+    CU(cudaGetLastError());
+    ++launches;
+    dev_iq = b->d_dcc_out;
+  }
   CU(cudaEventRecord(b->ev_m0[slot], s));
   for (const Group& g : b->groups) {
     MainParams p;
@@ -238,7 +250,7 @@ int enqueue_block(aeroddc_bank* b, const void* dev_iq) {
     p.err = b->d_err;
     if (g.Q > 1) CU(cudaMemsetAsync(g.d_flags, 0, sizeof(int) * (size_t)p.ngroups * g.nseg, s));
     dim3 grid((unsigned)(p.ngroups * (1 + g.Q * g.nseg)));
-    CU(launch_main(g.parent < 0 ? b->fmt : AERODDC_CF32, std::min(g.D, kFastStages), p, grid, s, b->mode == AERODDC_MODE_FAST));
+    CU(launch_main((g.parent < 0 && !b->dcc) ? b->fmt : AERODDC_CF32, std::min(g.D, kFastStages), p, grid, s, b->mode == AERODDC_MODE_FAST));
     ++launches;
   }
   CU(cudaEventRecord(b->ev_m1[slot], s));
@@ -321,6 +333,13 @@ int aeroddc_bank_set_mode(aeroddc_bank* b, int mode) {
   if (b->blocks_submitted > 0) return fail(AERODDC_ERR_STATE, "the arithmetic mode cannot change once blocks were processed");
   if (mode != AERODDC_MODE_EXACT && mode != AERODDC_MODE_FAST) return fail(AERODDC_ERR_ARG, "unknown mode %d", mode);
   b->mode = mode;
+  return AERODDC_OK;
+}
+
+int aeroddc_bank_set_dc_correction(aeroddc_bank* b, int enable) {
+  if (!b) return fail(AERODDC_ERR_ARG, "NULL bank");
+  if (b->finalized) return fail(AERODDC_ERR_STATE, "set DC correction before finalize");
+  b->dcc = enable != 0;
   return AERODDC_OK;
 }
 
@@ -529,6 +548,12 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
   CU(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
   CU(dmalloc((void**)&b->d_tail, sizeof(TailVfo) * nv));
   CU(cudaMemcpy(b->d_tail, h_tail.data(), sizeof(TailVfo) * nv, cudaMemcpyHostToDevice));
+
+  if (b->dcc) {
+    CU(dmalloc((void**)&b->d_dcc_out, sizeof(float) * 2 * (size_t)b->B));
+    CU(dmalloc((void**)&b->d_dcc_state, sizeof(float) * 2));
+    CU(cudaMemset(b->d_dcc_state, 0, sizeof(float) * 2));
+  }
 
   // ---- input staging ----
   b->in_bytes = (size_t)b->B * raw_bytes(b->fmt);

@@ -129,6 +129,12 @@ int aeroddc_fleet_set_mode(aeroddc_fleet* f, int mode) {
   return AERODDC_OK;
 }
 
+int aeroddc_fleet_set_dc_correction(aeroddc_fleet* f, int enable) {
+  if (!f) return aeroddc_set_error(AERODDC_ERR_ARG, "NULL fleet");
+  for (aeroddc_bank* b : f->banks) FOK(aeroddc_bank_set_dc_correction(b, enable));   // every GPU removes DC from its copy
+  return AERODDC_OK;
+}
+
 int aeroddc_fleet_finalize(aeroddc_fleet* f) {
   if (!f) return aeroddc_set_error(AERODDC_ERR_ARG, "NULL fleet");
   if (f->finalized) return aeroddc_set_error(AERODDC_ERR_STATE, "already finalized");

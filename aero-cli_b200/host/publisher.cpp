@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <stdexcept>
 
 #include "ini.h"
 
@@ -27,8 +28,7 @@ Publisher::Publisher(const std::string& deviceStr, bool enableBiast_, bool enabl
     return;
   }
   try {
-    // DC correction needs float samples on the host, so the bank then ingests cf32
-    const int fmt = enableDcc ? AERODDC_CF32 : source->format();
+    const int fmt = source->format();
     // GPUs: "gpus=N" in the device string (or AERODDC_GPUS) shards the VFOs over devices 0..N-1 (NCCL broadcast of each block)
     int ngpu = 1;
     const size_t gp = deviceStr.find("gpus=");
@@ -37,6 +37,7 @@ Publisher::Publisher(const std::string& deviceStr, bool enableBiast_, bool enabl
     std::vector<int> devs;
     for (int i = 0; i < std::max(1, ngpu); ++i) devs.push_back(i);
     bank = std::make_shared<aero::DdcBank>(Fs, buflen / 2, fmt, devs);
+    if (enableDcc && aeroddc_fleet_set_dc_correction(bank->handle(), 1) != AERODDC_OK) throw std::runtime_error(aeroddc_last_error());   // publisher.cpp:292-296, on the GPU
     for (vfo* m : VFOmain) m->addToBank(bank, -1);
     for (vfo* f : VFOflat) f->addToBank(bank, -1);
     bank->finalize();
@@ -192,31 +193,14 @@ void Publisher::wait() { if (mainReader.joinable()) mainReader.join(); }
 void Publisher::readerThread() {
   void* slot[2] = {nullptr, nullptr};
   size_t bytes = 0;
-  std::vector<unsigned char> raw;
   if (!running) goto Exit;
   for (int i = 0; i < 2; ++i)
     if (aeroddc_fleet_host_slot(bank->handle(), i, &slot[i], &bytes) != AERODDC_OK) { error = aeroddc_last_error(); goto Exit; }
-  if (enableDcc) raw.resize((size_t)(buflen / 2) * aero::formatBytes(source->format()));
   while (running) {
     void* dst = slot[blocks & 1];   // the source writes straight into the pinned ring
-    if (!source->read(enableDcc ? (void*)raw.data() : dst, (size_t)buflen / 2)) {
+    if (!source->read(dst, (size_t)buflen / 2)) {
       // "SoapySDR could not read stream from SDR" in the reference (publisher.cpp:269-272): end of stream
       break;
-    }
-    if (enableDcc) {   // publisher.cpp:288-299: convert to float, first-order DC removal, on the host like the reference
-      float* out = (float*)dst;
-      const size_t n = (size_t)buflen / 2;
-      for (size_t i = 0; i < n; ++i) {
-        float re, im;
-        if (source->format() == AERODDC_CU8) { re = ((float)raw[2 * i] - 127.4f) / 128.0f; im = ((float)raw[2 * i + 1] - 127.4f) / 128.0f; }
-        else if (source->format() == AERODDC_CS16) { re = (float)((int16_t*)raw.data())[2 * i] / 32768.0f; im = (float)((int16_t*)raw.data())[2 * i + 1] / 32768.0f; }
-        else { re = ((float*)raw.data())[2 * i]; im = ((float*)raw.data())[2 * i + 1]; }
-        cpx_typef curr(re, im);
-        avept = avept * (1.0f - 0.000001f) + 0.000001f * curr;
-        curr -= avept;
-        out[2 * i] = curr.real();
-        out[2 * i + 1] = curr.imag();
-      }
     }
     try {
       demodData(dst);

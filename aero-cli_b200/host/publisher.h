@@ -64,8 +64,6 @@ class Publisher {
   std::vector<vfo*> VFOflat;      // VFOs of a file without [main_vfos]: fed by the raw stream (see loadSettings)
   std::unique_ptr<aero::IqSource> source;
   std::shared_ptr<aero::DdcBank> bank;
-  std::vector<float> dccBuf;
-  cpx_typef avept = 0;            // DC-removal state (function-static in the reference, publisher.cpp:293)
   std::string error;
   long long blocks = 0;
 };

@@ -74,6 +74,12 @@ int aeroddc_bank_create(aeroddc_bank **out, int sample_rate, int block_len, int 
 enum { AERODDC_MODE_EXACT = 0, AERODDC_MODE_FAST = 1 };
 int aeroddc_bank_set_mode(aeroddc_bank *bank, int mode);
 
+/* Optional DC removal on the raw stream before any VFO, as Publisher::demodData does with --enable-dcc /
+ * correct_dc_bias=1 (publisher.cpp:292-296): avept = avept*(1-1e-6f) + 1e-6f*x; x -= avept, per rail, float32.
+ * The recurrence is sequential and is executed as such (one GPU thread per rail, ~8 cycles per sample: negligible
+ * at the reference's rates, about 60 ms per block at 61.44 MS/s). Call before finalize. */
+int aeroddc_bank_set_dc_correction(aeroddc_bank *bank, int enable);
+
 /* Append a VFO; returns its index (>= 0) or a negative error code.
  * Replaces: `new vfo()` + setters in publisher.cpp:121-147 and :159-217. */
 int aeroddc_bank_add_vfo(aeroddc_bank *bank, const aeroddc_vfo_desc *desc);
@@ -161,6 +167,7 @@ typedef struct aeroddc_fleet aeroddc_fleet;
 int aeroddc_fleet_create(aeroddc_fleet **out, int sample_rate, int block_len, int in_format, const int *devices, int n_devices);
 int aeroddc_fleet_add_vfo(aeroddc_fleet *fleet, const aeroddc_vfo_desc *desc);   /* desc->parent is a global index */
 int aeroddc_fleet_set_mode(aeroddc_fleet *fleet, int mode);
+int aeroddc_fleet_set_dc_correction(aeroddc_fleet *fleet, int enable);
 int aeroddc_fleet_finalize(aeroddc_fleet *fleet);
 /* Pinned host slot 0/1 of the ingest GPU's ring (fill it directly to avoid a host copy). */
 int aeroddc_fleet_host_slot(aeroddc_fleet *fleet, int slot, void **ptr, size_t *bytes);

@@ -140,6 +140,22 @@ void ddc_unpack(int fmt, const void *raw, long long n_complex, float *out) {
   }
 }
 
+/* Publisher::demodData's optional DC removal (publisher.cpp:292-296), in place on interleaved float I,Q:
+ *   avept = avept * (1.0f - 0.000001f) + 0.000001f * curr;  curr -= avept;   (std::complex<float>: per rail)
+ * state[2] is the running average (function-static in the reference). PARITY UNPINNED for this function:
+ * publisher.cpp cannot be compiled here (Qt, SoapySDR), so it is a restatement checked by reading only. */
+void ddc_dc_correct(float *iq, long long n_complex, float *state) {
+  const float k = 1.0f - 0.000001f, c = 0.000001f;
+  for (long long i = 0; i < n_complex; i++)
+    for (int r = 0; r < 2; r++) {
+      float x = iq[2 * i + r];
+      float t0 = state[r] * k;
+      float t1 = c * x;
+      state[r] = t0 + t1;
+      iq[2 * i + r] = x - state[r];
+    }
+}
+
 /* ------------------------------------------------------------------------------------------
  * One VFO
  * ---------------------------------------------------------------------------------------- */

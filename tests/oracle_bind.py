@@ -48,6 +48,7 @@ def oracle_lib():
         L.ddc_hilbert_taps.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         L.ddc_nco_table.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
         L.ddc_unpack.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]
+        L.ddc_dc_correct.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]
         _oracle = L
     return _oracle
 
@@ -225,6 +226,12 @@ def unpack(fmt, raw):
     out = np.empty(2 * n, np.float32)
     oracle_lib().ddc_unpack(fmt, raw.ctypes.data, n, out.ctypes.data)
     return out
+
+
+def dc_correct(iq_f32, state):
+    """In-place DC removal (publisher.cpp:292-296) of an interleaved float32 block; state = float32[2] running average."""
+    oracle_lib().ddc_dc_correct(iq_f32.ctypes.data, iq_f32.size // 2, state.ctypes.data)
+    return iq_f32
 
 
 def fnv1a64(data, h=1469598103934665603):

@@ -378,3 +378,34 @@ def test_many_vfos_three_decimations_two_formats():
         for j, i in enumerate(picks):
             assert bank.output(i)[0] == oracles[j].process(x), (i, b)
     bank.close()
+
+
+@pytest.mark.parametrize("fmt", [FMT_CU8, FMT_CF32])
+def test_dc_correction_vs_oracle(fmt):
+    """--enable-dcc / correct_dc_bias=1: the sequential first-order DC removal of Publisher::demodData
+    (publisher.cpp:292-296) on the GPU, state carried across blocks, then the normal chain."""
+    from oracle_bind import dc_correct
+
+    a = _aeroddc()
+    fs, blk = 288000, 57600
+    vfos = [dict(mixer=1234.0, D=2, L=0, gain=0.5), dict(mixer=-40000.0, D=1, L=6, gain=0.4)]
+    bank = a.Bank(fs, blk, fmt, 0)
+    for i, v in enumerate(vfos):
+        bank.add_vfo(v["mixer"], v["D"], v.get("L", 0), 0, v["gain"], 1, 1, 1, "DCC%02d" % i)
+    bank.set_dc_correction(True)
+    bank.finalize()
+    oracles = make_oracles(fs, blk, vfos)
+    state = np.zeros(2, np.float32)
+    for b in range(4):
+        raw = synth_raw(fmt, b * blk, blk, seed=9, amp=0.6)
+        if fmt == FMT_CF32:                              # a DC offset worth removing, on the I rail
+            raw[0::2] += np.float32(0.11)
+        else:
+            raw[0::2] = np.clip(raw[0::2].astype(np.int32) + 14, 0, 255).astype(np.uint8)
+        x = (raw if fmt == FMT_CF32 else unpack(fmt, raw)).copy()
+        dc_correct(x, state)
+        bank.process(raw)
+        for i, o in enumerate(oracles):
+            assert bank.output(i)[0] == o.process(x), (i, b)
+    assert abs(float(state[0])) > 1e-4                    # the average really moved
+    bank.close()
