@@ -48,6 +48,7 @@ ABI_SYMBOLS = [
     "aeroddc_fleet_create", "aeroddc_fleet_add_vfo", "aeroddc_fleet_set_mode", "aeroddc_fleet_finalize", "aeroddc_fleet_host_slot",
     "aeroddc_fleet_submit", "aeroddc_fleet_wait", "aeroddc_fleet_process", "aeroddc_fleet_output", "aeroddc_fleet_num_devices",
     "aeroddc_fleet_device_of", "aeroddc_fleet_destroy", "aeroddc_bank_set_dc_correction", "aeroddc_fleet_set_dc_correction",
+    "aeroddc_dev_alloc", "aeroddc_dev_free", "aeroddc_dev_upload", "aeroddc_ipc_export", "aeroddc_ipc_import", "aeroddc_ipc_close", "aeroddc_enable_peer",
 ]
 
 _lib = None
@@ -82,6 +83,13 @@ def lib():
         L.aeroddc_bank_set_mode.argtypes = [vp, ci]
         L.aeroddc_bank_set_dc_correction.argtypes = [vp, ci]
         L.aeroddc_fleet_set_dc_correction.argtypes = [vp, ci]
+        L.aeroddc_dev_alloc.argtypes = [ci, cz, ctypes.POINTER(vp)]
+        L.aeroddc_dev_free.argtypes = [ci, vp]
+        L.aeroddc_dev_upload.argtypes = [ci, vp, vp, cz]
+        L.aeroddc_ipc_export.argtypes = [ci, vp, ctypes.c_char_p]
+        L.aeroddc_ipc_import.argtypes = [ci, ctypes.c_char_p, ctypes.POINTER(vp)]
+        L.aeroddc_ipc_close.argtypes = [ci, vp]
+        L.aeroddc_enable_peer.argtypes = [ci, ci]
         L.aeroddc_fleet_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ctypes.POINTER(ci), ci]
         L.aeroddc_fleet_add_vfo.argtypes = [vp, ctypes.POINTER(VfoDesc)]
         L.aeroddc_fleet_set_mode.argtypes = [vp, ci]
@@ -131,6 +139,43 @@ def design_rotation(fs, freq):
     c, s = ctypes.c_float(), ctypes.c_float()
     _check(lib().aeroddc_design_rotation(fs, freq, ctypes.byref(c), ctypes.byref(s)))
     return c.value, s.value
+
+
+def dev_alloc(device, nbytes):
+    p = ctypes.c_void_p()
+    _check(lib().aeroddc_dev_alloc(device, nbytes, ctypes.byref(p)))
+    return p.value
+
+
+def dev_free(device, ptr):
+    _check(lib().aeroddc_dev_free(device, ptr))
+
+
+def dev_upload(device, ptr, array):
+    a = np.ascontiguousarray(array)
+    _check(lib().aeroddc_dev_upload(device, ptr, a.ctypes.data, a.nbytes))
+
+
+def ipc_export(device, ptr):
+    """64-byte CUDA IPC handle of a block allocated with dev_alloc in this process."""
+    buf = ctypes.create_string_buffer(64)
+    _check(lib().aeroddc_ipc_export(device, ptr, buf))
+    return buf.raw
+
+
+def ipc_import(device, handle):
+    """Device address, valid on `device` of THIS process, of a block another process exported."""
+    p = ctypes.c_void_p()
+    _check(lib().aeroddc_ipc_import(device, handle, ctypes.byref(p)))
+    return p.value
+
+
+def enable_peer(device, peer):
+    _check(lib().aeroddc_enable_peer(device, peer))
+
+
+def ipc_close(device, ptr):
+    _check(lib().aeroddc_ipc_close(device, ptr))
 
 
 def measure_fp32_peak(device=0):

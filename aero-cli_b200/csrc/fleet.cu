@@ -236,6 +236,55 @@ int aeroddc_fleet_device_of(aeroddc_fleet* f, int vfo) {
   return f->where[vfo].dev;
 }
 
+int aeroddc_dev_alloc(int device, size_t bytes, void** dev_ptr) {
+  if (!dev_ptr) return aeroddc_set_error(AERODDC_ERR_ARG, "NULL argument");
+  FCU(cudaSetDevice(device));
+  FCU(cudaMalloc(dev_ptr, bytes));
+  return AERODDC_OK;
+}
+int aeroddc_dev_free(int device, void* dev_ptr) {
+  FCU(cudaSetDevice(device));
+  FCU(cudaFree(dev_ptr));
+  return AERODDC_OK;
+}
+int aeroddc_dev_upload(int device, void* dev_ptr, const void* host, size_t bytes) {
+  FCU(cudaSetDevice(device));
+  FCU(cudaMemcpy(dev_ptr, host, bytes, cudaMemcpyHostToDevice));
+  return AERODDC_OK;
+}
+int aeroddc_ipc_export(int device, void* dev_ptr, unsigned char handle[AERODDC_IPC_HANDLE_BYTES]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == AERODDC_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+  FCU(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  FCU(cudaIpcGetMemHandle(&h, dev_ptr));
+  memcpy(handle, &h, sizeof h);
+  return AERODDC_OK;
+}
+int aeroddc_ipc_import(int device, const unsigned char handle[AERODDC_IPC_HANDLE_BYTES], void** dev_ptr) {
+  if (!dev_ptr) return aeroddc_set_error(AERODDC_ERR_ARG, "NULL argument");
+  FCU(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  FCU(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return AERODDC_OK;
+}
+int aeroddc_ipc_close(int device, void* dev_ptr) {
+  FCU(cudaSetDevice(device));
+  FCU(cudaIpcCloseMemHandle(dev_ptr));
+  return AERODDC_OK;
+}
+
+int aeroddc_enable_peer(int device, int peer) {
+  FCU(cudaSetDevice(device));
+  int can = 0;
+  FCU(cudaDeviceCanAccessPeer(&can, device, peer));
+  if (!can) return aeroddc_set_error(AERODDC_ERR_CUDA, "device %d cannot access device %d", device, peer);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return AERODDC_OK; }
+  FCU(e);
+  return AERODDC_OK;
+}
+
 void aeroddc_fleet_destroy(aeroddc_fleet* f) {
   if (!f) return;
   for (size_t i = 0; i < f->streams.size(); ++i) {

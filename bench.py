@@ -201,6 +201,9 @@ def main():
     ap.add_argument("--vfos", type=int, default=N_VFOS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast", action="store_true", help="skip the tolerance-mode side measurement")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1, device-resident value: 'peer' = every GPU's kernel pulls the raw tiles straight out of rank 0's HBM "
+                         "over NVLink (CUDA IPC mapping, fused with the compute); 'nccl' = ncclBroadcast into a local buffer first")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
 
@@ -249,6 +252,22 @@ def main():
             (src if world > 1 else dbuf)[i].copy_(torch.from_numpy(host[i]))
     torch.cuda.synchronize()
 
+    # N > 1, --exchange peer: rank 0's two source blocks live in plain cudaMalloc memory exported over CUDA IPC;
+    # every other rank maps them and hands the PEER address to its bank, whose TMA tile loads then read rank 0's
+    # HBM across NVLink while computing (no broadcast step, no staging buffer).
+    peer_ptr = None
+    if world > 1 and args.exchange == "peer":
+        handles = [None, None]
+        own = []
+        if rank == 0:
+            for i in range(2):
+                ptr = aeroddc.dev_alloc(local_rank, host[i].nbytes)
+                aeroddc.dev_upload(local_rank, ptr, host[i])
+                own.append(ptr)
+                handles[i] = aeroddc.ipc_export(local_rank, ptr)
+        dist.broadcast_object_list(handles, src=0)
+        peer_ptr = own if rank == 0 else [aeroddc.ipc_import(local_rank, h) for h in handles]
+
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
@@ -264,7 +283,7 @@ def main():
 
     def prefetch(k, from_host):
         """Start moving block k into this rank's HBM buffer k % nbuf (async)."""
-        if world == 1:
+        if world == 1 or (peer_ptr is not None and not from_host):
             return
         b = k % nbuf
         if rank == 0:
@@ -292,6 +311,8 @@ def main():
                     bank.submit(host[k & 1])
                 else:
                     bank.submit_device(dbuf[k & 1].data_ptr(), None)
+            elif peer_ptr is not None and not from_host:
+                bank.submit_device(peer_ptr[k & 1], None)      # the kernel reads rank 0's HBM directly
             else:
                 b = k % nbuf
                 bank.submit_device(dbuf[b].data_ptr(), events[b].cuda_event)
@@ -391,7 +412,7 @@ def main():
                             % (args.vfos, len(mine), BLOCK),
                 "n_vfos": args.vfos, "block_len": BLOCK, "sample_rate": FS,
                 "l2": "two alternating 123 MB raw blocks (246 MB > 126 MB L2); no explicit flush",
-                "parallelism": "vfo-shard x%d, NCCL broadcast of the raw block" % world if world > 1 else "single GPU",
+                "parallelism": ("vfo-shard x%d, raw block read from rank 0's HBM over NVLink inside the kernel (peer memory); e2e leg: NCCL broadcast" % world if args.exchange == "peer" else "vfo-shard x%d, NCCL broadcast of the raw block" % world) if world > 1 else "single GPU",
                 "realtime_x": value * 1e9 / (args.vfos * FS),
                 "finalize_s": t_finalize, "device_mb": bank.device_bytes() / 1e6,
                 "flop_per_vfo_sample": FLOPS_TOTAL,

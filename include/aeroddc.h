@@ -181,6 +181,23 @@ int aeroddc_fleet_num_devices(aeroddc_fleet *fleet);
 int aeroddc_fleet_device_of(aeroddc_fleet *fleet, int vfo);   /* index into the devices[] given at create */
 void aeroddc_fleet_destroy(aeroddc_fleet *fleet);
 
+/* ------------------------------------------------------------------------------------------------
+ * Peer-memory exchange for one-process-per-GPU deployments. aeroddc_bank_submit_device accepts ANY device
+ * address the GPU can read - including a block that lives in another GPU's HBM: the main kernel's TMA tile
+ * loads then pull the raw samples across NVLink tile by tile while it computes, and no separate broadcast
+ * step or staging copy exists. These helpers create such a block in one process and map it in the others
+ * (CUDA IPC): export on the owner, send the 64-byte handle through any channel, import on the peers.
+ * ---------------------------------------------------------------------------------------------- */
+#define AERODDC_IPC_HANDLE_BYTES 64
+int aeroddc_dev_alloc(int device, size_t bytes, void **dev_ptr);
+int aeroddc_dev_free(int device, void *dev_ptr);
+int aeroddc_dev_upload(int device, void *dev_ptr, const void *host, size_t bytes);   /* synchronous H2D */
+int aeroddc_ipc_export(int device, void *dev_ptr, unsigned char handle[AERODDC_IPC_HANDLE_BYTES]);
+int aeroddc_ipc_import(int device, const unsigned char handle[AERODDC_IPC_HANDLE_BYTES], void **dev_ptr);
+int aeroddc_ipc_close(int device, void *dev_ptr);
+/* Same process, two devices: let `device` read `peer`'s memory (cudaDeviceEnablePeerAccess; idempotent). */
+int aeroddc_enable_peer(int device, int peer);
+
 /* Host-side coefficient designers, exposed so that callers and tests can inspect exactly the taps
  * the bank uploads. Pure CPU code (no device needed), bit-identical to firfilter::low_pass with the
  * Hamming window (firfilter.cpp:46-99,186-193), FIRHilbert::FIRHilbert (dsp.cpp:181-215) and the

@@ -81,3 +81,34 @@ def test_fleet_keeps_sub_vfos_with_their_main_vfo(ndev):
             m.process(x)
             assert fleet.output(idx)[0] == s_.process(m.stage(3)), (idx, b)
     fleet.close()
+
+
+def test_bank_reads_its_block_from_a_peer_gpu():
+    """aeroddc_bank_submit_device with an address in ANOTHER GPU's HBM: the kernel's TMA tile loads cross NVLink.
+    Bytes must equal those of the same bank fed from local memory."""
+    import aeroddc
+
+    if _ndev() < 2:
+        pytest.skip("needs 2 GPUs")
+    fs, blk = 1536000, 384000
+    descs = _descs(fs, 9, 11)
+    banks = []
+    for dev in (1, 1):
+        b = aeroddc.Bank(fs, blk, aeroddc.CF32, dev)
+        for i, d in enumerate(descs):
+            b.add_vfo(d["mixer"], d["D"], 0, 0, d["gain"], 1, 1, 1, "P%04d" % i)
+        b.finalize()
+        banks.append(b)
+    aeroddc.enable_peer(1, 0)
+    remote = aeroddc.dev_alloc(0, blk * 8)          # lives on GPU 0, read by the bank on GPU 1
+    for k in range(3):
+        x = synth_raw(FMT_CF32, k * blk, blk, seed=4, amp=0.8)
+        aeroddc.dev_upload(0, remote, x)
+        banks[0].submit_device(remote)
+        banks[0].wait()
+        banks[1].process(x)
+        for i in range(len(descs)):
+            assert banks[0].output(i) == banks[1].output(i), (i, k)
+    aeroddc.dev_free(0, remote)
+    for b in banks:
+        b.close()
