@@ -283,7 +283,7 @@ def main():
 
     def prefetch(k, from_host):
         """Start moving block k into this rank's HBM buffer k % nbuf (async)."""
-        if world == 1 or (peer_ptr is not None and not from_host):
+        if world == 1:
             return
         b = k % nbuf
         if rank == 0:
@@ -296,10 +296,12 @@ def main():
         e.record()
         events[b] = e
 
-    def run_blocks(n, from_host, on_wait=None):
+    def run_blocks(n, from_host, on_wait=None, allow_peer=True):
         """n blocks, two in flight. from_host: the host-facing path (pinned host blocks, H2D inside)."""
+        peer = peer_ptr is not None and not from_host and allow_peer
         for k in range(min(2, n)):
-            prefetch(k, from_host)
+            if not peer:
+                prefetch(k, from_host)
         inflight = 0
         for k in range(n):
             if inflight == 2:
@@ -311,7 +313,7 @@ def main():
                     bank.submit(host[k & 1])
                 else:
                     bank.submit_device(dbuf[k & 1].data_ptr(), None)
-            elif peer_ptr is not None and not from_host:
+            elif peer:
                 bank.submit_device(peer_ptr[k & 1], None)      # the kernel reads rank 0's HBM directly
             else:
                 b = k % nbuf
@@ -365,11 +367,13 @@ def main():
         fbank.set_mode(aeroddc.MODE_FAST)
         fbank.finalize()
         main_bank, bank = bank, fbank
-        run_device(args.warmup)
+        run_blocks(args.warmup, False, allow_peer=False)
         sync_all()
         fast_main = []
         bank.stopwatch_start(False)
-        run_blocks(args.steps, False, on_wait=lambda: fast_main.append(bank.last_main_ms()))
+        # the tolerance mode consumes raw samples ~1.6x faster; at 8 GPUs seven peers pulling from rank 0 would saturate its
+        # NVLink egress, so this side measurement distributes the block with the NCCL broadcast instead
+        run_blocks(args.steps, False, on_wait=lambda: fast_main.append(bank.last_main_ms()), allow_peer=False)
         fast_ms = bank.stopwatch_stop()
         sync_all()
         fbank.close()
