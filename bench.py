@@ -226,6 +226,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- bank: this rank's VFO shard (v mod world) ----
@@ -424,7 +425,7 @@ def main():
             "e2e": {"value": e2e, "unit": "Gsps", "h2d_bytes_per_step": BLOCK * 8,
                     "d2h_bytes_per_step": int(args.vfos * (BLOCK >> DECIM) // LATE * 2),
                     "note": "aeroddc_bank_submit/wait with pinned host blocks, two blocks in flight; wall clock between device syncs"},
-            "gpu_launches": int(launches_per_step * args.steps * 2),
+            "gpu_launches": int(launches_per_step * args.steps * (2 if fast_ms is None else 3)),
             "roofline": {
                 "bound": "fp32", "kernel": "ddc_main_kernel", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                 "frac": achieved / peak_tflops, "traffic": traffic,
