@@ -22,6 +22,10 @@ class AeroDdcError(RuntimeError):
     pass
 
 
+class SegmentPlan(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("warmup", "boundary_warmup", "segment_len", "n_segments", "parts", "part_len", "vfo_groups", "ctas")]
+
+
 class VfoDesc(ctypes.Structure):
     _fields_ = [
         ("mixer_freq", ctypes.c_double),
@@ -48,7 +52,7 @@ ABI_SYMBOLS = [
     "aeroddc_fleet_create", "aeroddc_fleet_add_vfo", "aeroddc_fleet_set_mode", "aeroddc_fleet_finalize", "aeroddc_fleet_host_slot",
     "aeroddc_fleet_submit", "aeroddc_fleet_wait", "aeroddc_fleet_process", "aeroddc_fleet_output", "aeroddc_fleet_num_devices",
     "aeroddc_fleet_device_of", "aeroddc_fleet_destroy", "aeroddc_bank_set_dc_correction", "aeroddc_fleet_set_dc_correction",
-    "aeroddc_dev_alloc", "aeroddc_dev_free", "aeroddc_dev_upload", "aeroddc_ipc_export", "aeroddc_ipc_import", "aeroddc_ipc_close", "aeroddc_enable_peer",
+    "aeroddc_dev_alloc", "aeroddc_dev_free", "aeroddc_dev_upload", "aeroddc_ipc_export", "aeroddc_ipc_import", "aeroddc_ipc_close", "aeroddc_enable_peer", "aeroddc_plan_segments",
 ]
 
 _lib = None
@@ -90,6 +94,7 @@ def lib():
         L.aeroddc_ipc_import.argtypes = [ci, ctypes.c_char_p, ctypes.POINTER(vp)]
         L.aeroddc_ipc_close.argtypes = [ci, vp]
         L.aeroddc_enable_peer.argtypes = [ci, ci]
+        L.aeroddc_plan_segments.argtypes = [ci, ci, ci, ci, ctypes.c_double, ci, ctypes.POINTER(SegmentPlan)]
         L.aeroddc_fleet_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ctypes.POINTER(ci), ci]
         L.aeroddc_fleet_add_vfo.argtypes = [vp, ctypes.POINTER(VfoDesc)]
         L.aeroddc_fleet_set_mode.argtypes = [vp, ci]
@@ -176,6 +181,13 @@ def enable_peer(device, peer):
 
 def ipc_close(device, ptr):
     _check(lib().aeroddc_ipc_close(device, ptr))
+
+
+def plan_segments(block_len, decim_count, n_vfos, n_sm=148, waves=1.0, parts=0):
+    """The bank's segmentation of one VFO group (host arithmetic only)."""
+    p = SegmentPlan()
+    _check(lib().aeroddc_plan_segments(block_len, decim_count, n_vfos, n_sm, waves, parts, ctypes.byref(p)))
+    return {n: getattr(p, n) for n, _ in SegmentPlan._fields_}
 
 
 def measure_fp32_peak(device=0):

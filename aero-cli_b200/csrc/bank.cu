@@ -328,6 +328,37 @@ int aeroddc_bank_create(aeroddc_bank** out, int sample_rate, int block_len, int 
   return AERODDC_OK;
 }
 
+int aeroddc_plan_segments(int block_len, int decim_count, int n_vfos, int n_sm, double waves, int parts, aeroddc_segment_plan* out) {
+  if (!out || block_len <= 0 || decim_count < 0 || decim_count > kMaxStages || n_vfos < 1 || n_sm < 1 || !(waves > 0))
+    return fail(AERODDC_ERR_ARG, "bad planning arguments");
+  const int D = decim_count;
+  const int cstep = ilcm(kChunk, 1 << D);
+  if (block_len % cstep) return fail(AERODDC_ERR_ARG, "block of %d samples is not a multiple of %d", block_len, cstep);
+  const int align = ilcm(kNcoStride, 1 << D);
+  out->warmup = D == 0 ? 0 : ((10 << D) + cstep - 1) / cstep * cstep;   // 10*(2^D - 1) samples reach the deepest stage's history
+  out->boundary_warmup = D == 0 ? 0 : (11 << D);                        // the next block's shifted history needs 11 samples per stage
+  const int groups = (n_vfos + kVfoPerCta - 1) / kVfoPerCta;
+  // One wave of CTAs (kCtasPerSm per SM) cuts the block into segments, each paying one warm-up of W samples.
+  // The warp scheduler favours some resident warps, so equal CTAs of a single wave finish at different times;
+  // each segment is therefore processed as Q chained parts by Q short CTAs (state handed over through HBM),
+  // which evens the load without further warm-ups.
+  const int target = std::max(1, (int)std::floor((double)kCtasPerSm * n_sm * waves / groups) - 1);   // -1: the boundary CTA
+  int S = (block_len + target - 1) / target;
+  S = std::max(S, std::max(4 * out->warmup, 4096));
+  S = (S + align - 1) / align * align;
+  out->segment_len = S;
+  out->n_segments = (block_len + S - 1) / S;
+  int Q = parts > 0 ? parts : 16;
+  const int pal = ilcm(kTile, 1 << D);
+  while (Q > 1 && S / Q < 8 * pal) --Q;   // keep parts long enough that the hand-over stays negligible
+  Q = std::min(Q, 60);
+  out->parts = Q;
+  out->part_len = ((S + Q - 1) / Q + pal - 1) / pal * pal;
+  out->vfo_groups = groups;
+  out->ctas = groups * (1 + Q * out->n_segments);
+  return AERODDC_OK;
+}
+
 int aeroddc_bank_set_mode(aeroddc_bank* b, int mode) {
   if (!b) return fail(AERODDC_ERR_ARG, "NULL bank");
   if (b->blocks_submitted > 0) return fail(AERODDC_ERR_STATE, "the arithmetic mode cannot change once blocks were processed");
@@ -414,29 +445,13 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
   b->vfo_pitch = (col + 3) & ~3;
   const char* env_waves = getenv("AERODDC_WAVES");
   const double waves = env_waves ? std::max(0.05, atof(env_waves)) : 1.0;
+  const char* env_parts = getenv("AERODDC_PARTS");
+  const int env_parts_n = env_parts ? std::max(1, atoi(env_parts)) : 0;
   for (Group& g : b->groups) {
-    const int align = ilcm(kNcoStride, 1 << g.D);
-    const int cstep = ilcm(kChunk, 1 << g.D);
-    g.W = g.D == 0 ? 0 : ((10 << g.D) + cstep - 1) / cstep * cstep;
-    g.Wb = g.D == 0 ? 0 : (11 << g.D);
-    const int nblk_y = (g.count + kVfoPerCta - 1) / kVfoPerCta;
-    // One wave of CTAs (kCtasPerSm per SM) cuts the block into segments, each paying one warm-up of W samples.
-    // The warp scheduler favours some resident warps, so equal CTAs of a single wave finish at different times;
-    // each segment is therefore processed as Q chained parts by Q short CTAs (state handed over through HBM),
-    // which evens the load without further warm-ups. AERODDC_WAVES / AERODDC_PARTS override.
-    const int target = std::max(1, (int)std::floor((double)kCtasPerSm * b->n_sm * waves / nblk_y) - 1);   // -1: the boundary CTA
-    int S = (g.blk_in + target - 1) / target;
-    S = std::max(S, std::max(4 * g.W, 4096));
-    S = (S + align - 1) / align * align;
-    g.S = S;
-    g.nseg = (g.blk_in + S - 1) / S;
-    const char* env_parts = getenv("AERODDC_PARTS");
-    int Q = env_parts ? std::max(1, atoi(env_parts)) : 16;
-    const int pal = ilcm(kTile, 1 << g.D);
-    while (Q > 1 && S / Q < 8 * pal) --Q;              // keep parts long enough that the hand-over stays negligible
-    Q = std::min(Q, 60);
-    g.Q = Q;
-    g.P = ((S + Q - 1) / Q + pal - 1) / pal * pal;
+    aeroddc_segment_plan pl;
+    const int rc = aeroddc_plan_segments(g.blk_in, g.D, g.count, b->n_sm, waves, env_parts_n, &pl);
+    if (rc != AERODDC_OK) return rc;
+    g.W = pl.warmup; g.Wb = pl.boundary_warmup; g.S = pl.segment_len; g.nseg = pl.n_segments; g.Q = pl.parts; g.P = pl.part_len;
   }
 
   for (Group& g : b->groups) {

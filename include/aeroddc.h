@@ -65,6 +65,20 @@ typedef struct aeroddc_vfo_desc {
  * buflen arithmetic of Publisher::loadSettings (publisher.cpp:93-100). */
 int aeroddc_bank_create(aeroddc_bank **out, int sample_rate, int block_len, int in_format, int device);
 
+/* How the bank cuts a block of one VFO group (VFOs sharing input stream and D) into work for the main kernel
+ * (pure host arithmetic, no device needed; exposed for inspection and tests). All lengths in input samples.
+ * Invariants: segment_len and part_len are multiples of lcm(256, 2^D); n_segments*segment_len >= block_len;
+ * parts*part_len >= segment_len; segment_len >= 4*warmup. */
+typedef struct aeroddc_segment_plan {
+  int warmup;           /* W = 10*2^D (rounded to the chunk): samples a segment re-processes to rebuild its history */
+  int boundary_warmup;  /* 11*2^D: samples the boundary CTA re-processes for the next block's shifted history     */
+  int segment_len, n_segments;
+  int parts, part_len;  /* each segment runs as `parts` chained CTAs of part_len samples                          */
+  int vfo_groups;       /* CTAs side by side: ceil(n_vfos / 128)                                                  */
+  int ctas;             /* grid size of the launch                                                                */
+} aeroddc_segment_plan;
+int aeroddc_plan_segments(int block_len, int decim_count, int n_vfos, int n_sm, double waves, int parts, aeroddc_segment_plan *out);
+
 /* Arithmetic mode of the half-band/mix/NCO kernel; call before the first block.
  *   AERODDC_MODE_EXACT (default): every multiply and add of the reference, un-fused, in its order:
  *       payloads are byte-identical to the reference's vfo::process chain.

@@ -92,3 +92,30 @@ def test_rotation_matches_oracle():
         c, s = ctypes.c_float(), ctypes.c_float()
         O.ddc_nco_rotation(fs, f, ctypes.byref(c), ctypes.byref(s))
         assert aeroddc.design_rotation(fs, f) == (c.value, s.value)
+
+
+def test_segment_plan_invariants():
+    """Host arithmetic that cuts a block into segments and chained parts (aeroddc_plan_segments)."""
+    import math
+
+    rng = np.random.default_rng(0)
+    cases = [(15360000, 8, 1024), (15360000, 8, 128), (384000, 5, 30), (57600, 1, 1), (60000, 0, 3), (480000, 3, 2), (5120, 8, 2)]
+    for _ in range(300):
+        D = int(rng.integers(0, 9))
+        step = math.lcm(32, 1 << D)
+        blk = step * int(rng.integers(max(1, (20 << D) // step + 1), 4000))
+        cases.append((blk, D, int(rng.integers(1, 3000))))
+    for blk, D, nv in cases:
+        for waves, parts in ((1.0, 0), (0.25, 1), (3.0, 5), (1.0, 60)):
+            p = aeroddc.plan_segments(blk, D, nv, 148, waves, parts)
+            al = math.lcm(256, 1 << D)
+            assert p["warmup"] % math.lcm(32, 1 << D) == 0 and p["warmup"] >= (10 * ((1 << D) - 1) if D else 0)
+            assert p["boundary_warmup"] == (11 << D if D else 0)
+            assert p["segment_len"] % al == 0 and p["part_len"] % al == 0
+            assert p["n_segments"] * p["segment_len"] >= blk > (p["n_segments"] - 1) * p["segment_len"]
+            assert p["parts"] >= 1 and p["parts"] * p["part_len"] >= p["segment_len"]
+            assert p["segment_len"] >= 4 * p["warmup"]
+            assert p["vfo_groups"] == -(-nv // 128)
+            assert p["ctas"] == p["vfo_groups"] * (1 + p["parts"] * p["n_segments"])
+    with pytest.raises(aeroddc.AeroDdcError):
+        aeroddc.plan_segments(57601, 1, 1)
