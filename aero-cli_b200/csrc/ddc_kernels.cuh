@@ -8,13 +8,15 @@
 //   usb_demod / usb_decimdemod   /root/reference/publish/vfo.cpp:188-258
 //   compress                     /root/reference/publish/vfo.cpp:260-287
 //
-// Design: one thread carries TWO VFOs through time in the two lanes of the
-// Blackwell packed-FP32 instructions (FMUL2/FADD2, PTX mul/add/sub.rn.f32x2). Every multiply and
-// add of the reference is issued un-fused and in the reference's order, so results are
-// bit-identical to the CPU chain; packing halves the issue slots per flop, which leaves room for
-// the shared-memory broadcast loads and register moves next to a saturated FP32 pipe.
-// The raw IQ tile is staged once per CTA in shared memory (TMA bulk copy) and broadcast to all
-// VFOs of the CTA; time is cut into segments, each warmed up over the 10*2^D samples before it.
+// Design: one thread carries ONE VFO through time; its I and Q rails sit in the two
+// lanes of the Blackwell packed-FP32 instructions (FMUL2/FFMA2, PTX mul/fma.rn.f32x2). Every multiply
+// and add of the reference is issued un-fused and in the reference's order, so results are
+// bit-identical to the CPU chain; packing halves the issue slots per flop, which leaves room for the
+// shared-memory broadcast loads and register moves next to a saturated FP32 pipe.
+// The raw IQ tile is staged once per CTA in shared memory (TMA bulk copy) and broadcast to the 128
+// VFOs of the CTA. Time is cut into segments (each warmed up over the 10*2^D samples before it) and
+// every segment into chained parts whose state is handed from CTA to CTA through HBM.
+// Only bank.cu includes this header (compute-only translation unit; no host-side state here).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
