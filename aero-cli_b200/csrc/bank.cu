@@ -246,9 +246,10 @@ int enqueue_block(aeroddc_bank* b, const void* dev_iq) {
     p.P = g.P;
     p.ngroups = (g.count + kVfoPerCta - 1) / kVfoPerCta;
     p.flags = g.d_flags;
+    p.ticket = g.d_flags + (size_t)p.ngroups * g.nseg;   // the counter lives behind the flags
     p.hand = g.d_hand;
     p.err = b->d_err;
-    if (g.Q > 1) CU(cudaMemsetAsync(g.d_flags, 0, sizeof(int) * (size_t)p.ngroups * g.nseg, s));
+    CU(cudaMemsetAsync(g.d_flags, 0, sizeof(int) * ((size_t)p.ngroups * g.nseg + 1), s));
     dim3 grid((unsigned)(p.ngroups * (1 + g.Q * g.nseg)));
     CU(launch_main((g.parent < 0 && !b->dcc) ? b->fmt : AERODDC_CF32, std::min(g.D, kFastStages), p, grid, s, b->mode == AERODDC_MODE_FAST));
     ++launches;
@@ -456,8 +457,8 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
 
   for (Group& g : b->groups) {
     const size_t nk = (size_t)((g.count + kVfoPerCta - 1) / kVfoPerCta) * g.nseg;
-    CU(cudaMalloc((void**)&g.d_flags, sizeof(int) * nk));
-    CU(cudaMemset(g.d_flags, 0, sizeof(int) * nk));
+    CU(cudaMalloc((void**)&g.d_flags, sizeof(int) * (nk + 1)));   // + the ticket counter
+    CU(cudaMemset(g.d_flags, 0, sizeof(int) * (nk + 1)));
     CU(cudaMalloc((void**)&g.d_hand, sizeof(float2) * nk * kHandSlots * kThreads));
   }
   CU(cudaHostAlloc((void**)&b->h_err, sizeof(int), cudaHostAllocMapped));

@@ -158,6 +158,7 @@ struct MainParams {
   // CTA (q, k) waits for flag[k] == q, loads the state CTA (q-1, k) left in `hand`, and passes it on (flag = q+1).
   int Q, P, ngroups;
   int* flags;                // [ngroups][nseg] parts completed; zeroed by the host before every launch
+  int* ticket;               // work-item counter, zeroed by the host before every launch
   float2* hand;              // [ngroups][nseg][kHandSlots][kThreads]
   int* err;                  // set to 1 if a chained CTA gave up waiting (should never happen)
 };
@@ -352,9 +353,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TS::kRawStages * TS::kRawBytes + TS::kCvtBytes + TS::kDeepBytes);
 
   const int tid = threadIdx.x;
-  // 1-D grid, dispatched in index order: [boundary CTA of every VFO group] then part 0 of every (group, segment),
-  // then part 1 of every (group, segment), ... so a CTA's predecessor in its chain always has a smaller index.
-  int bid = blockIdx.x;
+  // 1-D grid. Work items are numbered [boundary CTA of every VFO group], then part 0 of every (group, segment), then
+  // part 1 of every (group, segment), ... and a CTA takes the next number when it STARTS (atomic ticket), so the
+  // predecessor in its chain has always started before it - whatever order the hardware dispatches blocks in.
+  __shared__ int s_ticket;
+  if (tid == 0) s_ticket = atomicAdd(p.ticket, 1);
+  __syncthreads();
+  int bid = s_ticket;
   const bool is_boundary = bid < p.ngroups;
   int q = 0, gy = bid, seg = 0;
   if (!is_boundary) {
