@@ -127,6 +127,38 @@ def test_settings_errors(tmp_path):
     assert subprocess.run([BIN, "--plan", str(tmp_path / "missing.ini")], capture_output=True).returncode == 1
 
 
+def test_settings_reader_dialect(tmp_path):
+    """QSettings IniFormat details the deployed files rely on: an explicit [General] group is the top level, values may be
+    quoted, ';' and '#' start comment lines, CRLF line ends, unparsable integers read as 0 (QVariant::toInt)."""
+    _build()
+    plain = ("sample_rate=288000\ncenter_frequency=10000000\n[main_vfos]\nsize=1\n1\\frequency=10000000\n1\\out_rate=288000\n"
+             "[vfos]\nsize=1\n1\\frequency=10050000\n1\\data_rate=600\n1\\gain=150\n1\\filter_bandwidth=0\n1\\topic=AAA01\n")
+    fancy = ("; a comment\r\n# another\r\n[General]\r\n sample_rate = \"288000\" \r\ncenter_frequency=10000000\r\n\r\n[main_vfos]\r\nsize=1\r\n"
+             "1\\frequency=10000000\r\n1\\out_rate=288000\r\n[vfos]\r\n1\\topic=\"AAA01\"\r\nsize=1\r\n1\\frequency=10050000\r\n"
+             "1\\data_rate=600\r\n1\\gain=150\r\n1\\filter_bandwidth=wide\r\nnot a key line\r\n")
+    def plan(text):
+        p = tmp_path / "d.ini"
+        p.write_bytes(text.encode())
+        r = subprocess.run([BIN, "--plan", str(p)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        return json.loads(r.stdout)
+    assert plan(plain) == plan(fancy)
+    got = plan(plain)
+    assert [v["kind"] for v in got["vfos"]] == ["main", "sub"] and got["vfos"][1]["topic"] == "AAA01"
+
+
+def test_settings_main_vfo_limit(tmp_path):
+    """The reference holds its main VFOs' children in VFOsub[3] (publisher.h:50): a fourth main VFO is refused up front
+    instead of writing past the array."""
+    _build()
+    text = "sample_rate=1920000\ncenter_frequency=10000000\n[main_vfos]\nsize=4\n" + "".join(
+        "%d\\frequency=%d\n%d\\out_rate=240000\n" % (i, 9400000 + 300000 * i, i) for i in range(1, 5))
+    p = tmp_path / "m.ini"
+    p.write_text(text)
+    r = subprocess.run([BIN, "--plan", str(p)], capture_output=True, text=True)
+    assert r.returncode == 1 and "more than 3 main VFOs" in r.stdout + r.stderr
+
+
 def test_zmq_wire_format_over_a_real_socket():
     """ZmqPublisher through libzmq (dlopen) to a pyzmq SUB socket: three frames - 5 topic bytes, uint32 LE
     rate, payload - as aero-decode's consumer expects (zmqpublisher.cpp:61-73, decode/decode.cpp:283-366)."""
