@@ -177,9 +177,12 @@ def main():
     ap.add_argument("--bitrate", type=int, default=600, choices=[600, 1200])
     ap.add_argument("--messages", type=int, default=4)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--lead", type=int, default=6, help="fill-in frames before the first message: the receiver needs "
+                    "up to ~8 s to hunt to the carrier and lock (SignalHunter steps 450 Hz every 15 spectra)")
+    ap.add_argument("--tail", type=int, default=2)
     args = ap.parse_args()
     msgs = example_messages(args.messages, args.seed)
-    bits = PChannelFramer(args.bitrate).stream(messages_to_sus(msgs))
+    bits = PChannelFramer(args.bitrate).stream(messages_to_sus(msgs), args.lead, args.tail)
     bits.tofile(args.out)
     for m in msgs:
         print("AES=%06X GES=%02X REG=%s LABEL=%s TEXT=%s" % m)

@@ -2,29 +2,37 @@
 """Synthetic IQ capture generator (replaces SDR hardware for tests and benchmarks).
 
 Writes interleaved I,Q samples (cu8 / cs16 / cf32) containing AWGN plus MSK / OQPSK-like carriers at
-given offsets from the centre frequency. The carriers carry pseudo-random symbols, not valid AeroL
-frames (the reference ships only a decoder; a frame-exact modulator is out of scope) - they give the
-VFOs in-band energy of the right bandwidth so that parity is measured on realistic levels.
+given offsets from the centre frequency. By default a carrier carries pseudo-random symbols (in-band
+energy of the right bandwidth, so that parity is measured on realistic levels). An MSK carrier can
+instead carry a channel bit stream written by tools/aerol_frames.py (one byte per bit): that is a
+valid Aero-L P channel which the unchanged aero-decode demodulates and decodes.
 
     tools/synth_iq.py out.cu8 --format cu8 --rate 2400000 --seconds 2 \\
         --carrier 123456:10500:oqpsk:0.1 --carrier -400000:600:msk:0.05 --noise 0.05
+    tools/aerol_frames.py p600.bits --bitrate 600 --messages 3
+    tools/synth_iq.py out.cu8 --rate 288000 --seconds 20 --carrier 50650:600:msk:0.2:bits=p600.bits
 """
 import argparse
 
 import numpy as np
 
 
-def carrier(n0, n, fs, offset_hz, baud, kind, amp, seed, state):
-    """Samples n0..n0+n-1 of one constant-envelope carrier; `state` carries the MSK phase across calls."""
+def carrier(n0, n, fs, offset_hz, baud, kind, amp, seed, state, data_bits=None):
+    """Samples n0..n0+n-1 of one constant-envelope carrier; `state` carries the MSK phase across calls.
+    `data_bits` (0/1 array) replaces the pseudo-random symbols for as long as it lasts."""
     t = np.arange(n0, n0 + n, dtype=np.float64)
     sym = (t * baud / fs).astype(np.int64)
     # symbol k -> +-1 from a counter hash, so any block can be generated independently
     h = (sym.astype(np.uint64) + np.uint64(seed)) * np.uint64(0x9E3779B97F4A7C15)
     h ^= h >> np.uint64(31)
     bits = ((h >> np.uint64(17)) & np.uint64(1)).astype(np.float64) * 2 - 1
+    if data_bits is not None and len(data_bits):
+        have = sym < len(data_bits)
+        bits[have] = data_bits[sym[have]].astype(np.float64) * 2 - 1
     frac = t * baud / fs - sym
     if kind == "msk":
-        # MSK: the phase advances by +-pi/2 per symbol
+        # MSK: the phase advances by +-pi/2 per symbol; a one raises the frequency, which is the sense the
+        # reference's MskDemodulator + differential decoder expect behind the USB demodulator
         acc = state.get("acc", 0.0) + np.cumsum(bits) / max(fs / baud, 1.0)
         state["acc"] = float(acc[-1]) if n else state.get("acc", 0.0)
         ph = 0.5 * np.pi * acc
@@ -41,20 +49,24 @@ def main():
     ap.add_argument("--rate", type=int, default=2400000)
     ap.add_argument("--seconds", type=float, default=1.0)
     ap.add_argument("--noise", type=float, default=0.05, help="AWGN RMS per rail")
-    ap.add_argument("--carrier", action="append", default=[], help="offset_hz:baud:msk|oqpsk:amplitude")
+    ap.add_argument("--carrier", action="append", default=[], help="offset_hz:baud:msk|oqpsk:amplitude[:bits=FILE]")
     ap.add_argument("--seed", type=int, default=1)
     args = ap.parse_args()
     total = int(args.rate * args.seconds)
     blk = 1 << 20
     rng = np.random.default_rng(args.seed)
     states = [dict() for _ in args.carrier]
+    payloads = []
+    for c in args.carrier:
+        extra = c.split(":")[4:]
+        payloads.append(np.fromfile(extra[0][5:], np.uint8) if extra and extra[0].startswith("bits=") else None)
     with open(args.out, "wb") as f:
         for n0 in range(0, total, blk):
             n = min(blk, total - n0)
             x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) * args.noise
             for i, c in enumerate(args.carrier):
-                off, baud, kind, amp = c.split(":")
-                x += carrier(n0, n, args.rate, float(off), float(baud), kind, float(amp), args.seed * 1000 + i, states[i])
+                off, baud, kind, amp = c.split(":")[:4]
+                x += carrier(n0, n, args.rate, float(off), float(baud), kind, float(amp), args.seed * 1000 + i, states[i], payloads[i])
             iq = np.empty(2 * n, np.float64)
             iq[0::2], iq[1::2] = x.real, x.imag
             if args.format == "cf32":
