@@ -2,10 +2,10 @@
 the reference's UNCHANGED decoder and must yield the same decoded ACARS set as the CPU chain's payloads.
 
   tools/aerol_frames.py        ACARS text -> ISU/SSU signal units -> scrambler, K=7 code, interleaver, UW + header
-  tools/synth_iq.py            channel bits -> 600 bit/s MSK carriers inside a 288 kS/s cu8 capture
+  tools/synth_iq.py            channel bits -> 600 bit/s MSK or 10500 bit/s offset-QPSK carriers inside a 288 kS/s cu8 capture
   aero-publish-b200 --dump     the product (GPU) : capture -> per-topic int16 payloads            [-m gpu]
   tests/tools/oracle_payloads  the CPU chain     : capture -> per-topic int16 payloads
-  tests/tools/ref_decode.py    oracle/_ref/libref_decode.so = reference MskDemodulator + SignalHunter + AeroL,
+  tests/tools/ref_decode.py    oracle/_ref/libref_decode.so = reference Msk/OqpskDemodulator + SignalHunter + AeroL,
                                compiled unmodified (Qt and libcorrect replaced by shims, see oracle/ref_decode_harness.cpp)
 
 The decoder library is built in this container from /root/reference/decode and travels to the GPU box as a built
@@ -25,13 +25,20 @@ import aerol_frames as af  # noqa: E402
 import ref_decode  # noqa: E402
 
 BIN = os.path.join(ROOT, "aero-cli_b200", "aero-publish-b200")
-INI = os.path.join(ROOT, "tests", "data", "e2e_288k.ini")
+DATA = os.path.join(ROOT, "tests", "data")
 
 pytestmark = pytest.mark.skipif(not os.path.exists(ref_decode.LIB),
                                 reason="oracle/_ref/libref_decode.so not built (needs /root/reference/decode: make -C oracle refdecode)")
 
 # topic -> (carrier offset from the capture centre: VFO frequency - centre + audio offset, amplitude, message seed)
-CHANNELS = {"PCH01": (50000 + 650, 0.20, 1), "PCH02": (-70000 + 1100, 0.15, 2), "PCH03": (101000 + 650, 0.25, 3)}
+# The 1200 bit/s channel type is left out on purpose: Decoder::Decoder leaves the MSK demodulator's fb at its 600 bit/s
+# default and only switches Fs to 24000 (decode.cpp:141-145), so the unmodified chain does not lock to such a carrier.
+SCENARIOS = {
+    "msk600": dict(bitrate=600, kind="msk", ini=os.path.join(DATA, "e2e_288k.ini"), seconds=28, lead=6, messages=3,
+                   channels={"PCH01": (50000 + 650, 0.20, 1), "PCH02": (-70000 + 1100, 0.15, 2), "PCH03": (101000 + 650, 0.25, 3)}),
+    "oqpsk10500": dict(bitrate=10500, kind="aoqpsk", ini=os.path.join(DATA, "e2e_288k_oqpsk.ini"), seconds=8, lead=6, messages=8,
+                       channels={"WCH01": (60000 + 8000, 0.20, 4), "WCH02": (-80000 + 9000, 0.15, 5)}),
+}
 
 
 def expected_records(msgs):
@@ -45,12 +52,12 @@ def expected_records(msgs):
     return want
 
 
-@pytest.mark.parametrize("bitrate", [600, 1200])
+@pytest.mark.parametrize("bitrate", [600, 1200, 10500])
 def test_frame_generator_is_the_inverse_of_the_reference_frame_decoder(bitrate):
     """Channel bits (hard decisions as soft values 0 / 255) straight into the unmodified AeroL::processDemodulatedSoftBits."""
     msgs = af.example_messages(5, seed=7)
     bits = af.PChannelFramer(bitrate).stream(af.messages_to_sus(msgs))
-    assert bits.size % 1200 == 0
+    assert bits.size % (5250 if bitrate == 10500 else 1200) == 0
     dec = ref_decode.RefDecoder(bitrate)
     soft = bits.astype(np.int16) * 255
     for i in range(0, soft.size, 12):          # the demodulators emit 12 soft bits at a time (mskdemodulator.cpp:423-426)
@@ -78,48 +85,64 @@ def test_a_broken_crc_is_rejected_by_the_reference_decoder():
     assert got == expected_records([msgs[0]]) | {r.replace("QNO=01|REFNO=00", "QNO=03|REFNO=02") for r in expected_records([msgs[2]])}
 
 
-def _make_capture(tmp):
+def _make_capture(tmp, sc):
     sent = {}
     carriers = []
-    for topic, (offset, amp, seed) in CHANNELS.items():
-        msgs = af.example_messages(3, seed=seed)
+    for topic, (offset, amp, seed) in sc["channels"].items():
+        msgs = af.example_messages(sc["messages"], seed=seed)
         sent[topic] = msgs
-        bits = af.PChannelFramer(600).stream(af.messages_to_sus(msgs), lead_frames=6, tail_frames=2)
+        bits = af.PChannelFramer(sc["bitrate"]).stream(af.messages_to_sus(msgs), lead_frames=sc["lead"], tail_frames=3)
         path = tmp / (topic + ".bits")
         bits.tofile(path)
-        carriers.append("--carrier=%d:600:msk:%g:bits=%s" % (offset, amp, path))
+        carriers.append("--carrier=%d:%d:%s:%g:bits=%s" % (offset, sc["bitrate"], sc["kind"], amp, path))
     iq = tmp / "cap.cu8"
-    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "synth_iq.py"), str(iq), "--format", "cu8", "--rate", "288000", "--seconds", "28",
-                    "--noise", "0.02"] + carriers, check=True, capture_output=True)
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "synth_iq.py"), str(iq), "--format", "cu8", "--rate", "288000", "--seconds",
+                    str(sc["seconds"]), "--noise", "0.02"] + carriers, check=True, capture_output=True)
     return iq, sent
 
 
-def _cpu_dump(iq, out):
-    subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "oracle_payloads.py"), INI, str(iq), "cu8", str(out)], check=True, capture_output=True)
+def _cpu_dump(ini, iq, out):
+    subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "oracle_payloads.py"), ini, str(iq), "cu8", str(out)], check=True, capture_output=True)
 
 
-def test_cpu_chain_payloads_decode_to_every_sent_message(tmp_path):
-    """frames -> MSK -> wideband capture -> reference-exact CPU chain -> reference demodulator and decoder -> the messages.
-    Needs aero-publish-b200 only for --plan (settings-file arithmetic, no device)."""
-    iq, sent = _make_capture(tmp_path)
-    _cpu_dump(iq, tmp_path / "cpu")
-    got = ref_decode.decode_dump(str(tmp_path / "cpu"), 600)
-    assert sorted(got) == sorted(CHANNELS)
+def _decode(dump, bitrate):
+    """A fresh process per dump: the reference demodulators keep a few function-level statics (oqpskdemodulator.cpp:398-410),
+    so two decodes only start from the same state in separate processes - as two aero-decode runs would."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "ref_decode.py"), str(dump), str(bitrate)], check=True, capture_output=True,
+                       text=True)
+    out = {}
+    for line in r.stdout.splitlines():
+        topic, rec = line.split(" ", 1)
+        out.setdefault(topic, []).append(rec)
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_cpu_chain_payloads_decode_to_every_sent_message(tmp_path, name):
+    """frames -> modulator -> wideband capture -> reference-exact CPU chain -> reference demodulator and decoder -> the
+    messages. Needs aero-publish-b200 only for --plan (settings-file arithmetic, no device)."""
+    sc = SCENARIOS[name]
+    iq, sent = _make_capture(tmp_path, sc)
+    _cpu_dump(sc["ini"], iq, tmp_path / "cpu")
+    got = _decode(tmp_path / "cpu", sc["bitrate"])
+    assert sorted(got) == sorted(sc["channels"])
     for topic, msgs in sent.items():
         assert set(got[topic]) == expected_records(msgs), topic
 
 
 @pytest.mark.gpu
-def test_gpu_payloads_decode_to_the_identical_acars_set(tmp_path):
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_gpu_payloads_decode_to_the_identical_acars_set(tmp_path, name):
     """The same capture through the product (CUDA bank behind Publisher) and through the CPU chain: the unchanged decoder
     must produce identical record lists per topic - and they must be the messages that were sent."""
-    iq, sent = _make_capture(tmp_path)
+    sc = SCENARIOS[name]
+    iq, sent = _make_capture(tmp_path, sc)
     gpu, cpu = tmp_path / "gpu", tmp_path / "cpu"
     gpu.mkdir()
-    subprocess.run([BIN, "-d", "file=%s,format=cu8" % iq, "--dump", str(gpu), INI], check=True, capture_output=True)
-    _cpu_dump(iq, cpu)
-    from_gpu = ref_decode.decode_dump(str(gpu), 600)
-    from_cpu = ref_decode.decode_dump(str(cpu), 600)
+    subprocess.run([BIN, "-d", "file=%s,format=cu8" % iq, "--dump", str(gpu), sc["ini"]], check=True, capture_output=True)
+    _cpu_dump(sc["ini"], iq, cpu)
+    from_gpu = _decode(gpu, sc["bitrate"])
+    from_cpu = _decode(cpu, sc["bitrate"])
     assert from_gpu == from_cpu
     for topic, msgs in sent.items():
         assert set(from_gpu[topic]) == expected_records(msgs), topic

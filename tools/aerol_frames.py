@@ -13,11 +13,13 @@ inverse of each receive step, in transmit order:
     FEC         -> rate 1/2 K=7 convolutional code, polynomials 109 / 79 with the newest bit in the LSB, never
                    flushed between frames                 (AeroL::AeroL SetCode(2, 7, {109, 79}), aerol.cpp:910-914)
     interleaver -> 64 x N block, rows permuted by 27 i mod 64 (inverse of deinterleave_ba,     aerol.cpp:594-611;
-                   N = 6 at 600 bit/s, 9 at 1200 bit/s,    aerol.cpp:980-999)
-    framing     -> 32-bit unique word 0xE15AE893, 16-bit header (format id 1, super-frame marker, frame counter
-                   twice), 1152 channel bits = 1200 bits  (aerol.cpp:916-917, 1182-1222, 980-999)
+                   N = 6 at 600 bit/s, 9 at 1200 bit/s, 78 at 10500 bit/s, aerol.cpp:980-1021)
+    framing     -> 600 / 1200 bit/s (MSK): 32-bit unique word 0xE15AE893, 16-bit header (format id 1, super-frame
+                   marker, frame counter twice), 1152 channel bits = 1200 bits (aerol.cpp:916-917, 1182-1222);
+                   10500 bit/s (OQPSK): the unique word on both rails (64 bits, aerol.cpp:1091-1122,
+                   927-931), 16-bit header + 178 dummy bits, 4992 channel bits = 5250 bits (aerol.cpp:1012-1021)
 
-The channel bits then go to the MSK modulator in tools/synth_iq.py (`--carrier ...:bits=FILE`).
+The channel bits then go to the modulators in tools/synth_iq.py (`--carrier ...:msk|aoqpsk:...:bits=FILE`).
 """
 import numpy as np
 
@@ -97,14 +99,17 @@ def scrambler_sequence(n):
 
 
 class PChannelFramer:
-    """Turns a queue of 12-octet signal units into the channel bit stream of a 600 or 1200 bit/s P channel."""
+    """Turns a queue of 12-octet signal units into the channel bit stream of a 600, 1200 or 10500 bit/s P channel."""
 
     def __init__(self, bitrate):
-        assert bitrate in (600, 1200)
-        self.cols = 6 if bitrate == 600 else 9
+        assert bitrate in (600, 1200, 10500)
+        self.cols = {600: 6, 1200: 9, 10500: 78}[bitrate]
+        self.wide = bitrate == 10500
+        self.sus_per_frame = 26 if self.wide else 6          # 4992 / 2 / 96 or 1152 / 2 / 96
+        self.frame_bits = 5250 if self.wide else 1200
         self.reg = 0                  # convolutional encoder register, continuous across frames
         self.frame_no = 0
-        self.prbs = scrambler_sequence(576)
+        self.prbs = scrambler_sequence(96 * self.sus_per_frame)
         perm = (np.arange(ROWS) * 27) % ROWS
         k = np.arange(ROWS * self.cols)
         # receiver: out[j*64 + i] = block[perm[i]*cols + j]  ->  transmitter: block[perm[i]*cols + j] = coded[j*64 + i]
@@ -122,8 +127,8 @@ class PChannelFramer:
         return out
 
     def frame(self, sus):
-        """One 1200-bit frame from exactly six signal units."""
-        assert len(sus) == 6 and all(len(s) == 12 for s in sus)
+        """One frame from exactly `sus_per_frame` signal units."""
+        assert len(sus) == self.sus_per_frame and all(len(s) == 12 for s in sus)
         info = np.unpackbits(np.frombuffer(b"".join(sus), np.uint8), bitorder="little")
         coded = self._encode(info ^ self.prbs)
         data = np.empty_like(coded)
@@ -137,16 +142,20 @@ class PChannelFramer:
         self.frame_no += 1
         uw = [(UNIQUE_WORD >> (31 - n)) & 1 for n in range(32)]
         hd = [(header >> (15 - n)) & 1 for n in range(16)]
+        if self.wide:
+            uw = [b for b in uw for _ in (0, 1)]             # the same word on the I and on the Q rail
+            hd += [(n * 7 + n // 3) & 1 for n in range(178)]  # dummy bits (the receiver drops them)
         return np.concatenate([np.array(uw + hd, np.uint8), data])
 
     def stream(self, sus, lead_frames=2, tail_frames=2):
         """Channel bits for all `sus` (padded with fill-in units), with fill-in frames before and after: the receiver
         hands a frame over only while it receives the next one (Viterbi + delay line = one frame, aerol.cpp:1497-1509)."""
-        q = [fill_in_su()] * (6 * lead_frames) + list(sus)
-        while len(q) % 6:
+        n = self.sus_per_frame
+        q = [fill_in_su()] * (n * lead_frames) + list(sus)
+        while len(q) % n:
             q.append(fill_in_su())
-        q += [fill_in_su()] * (6 * tail_frames)
-        return np.concatenate([self.frame(q[i:i + 6]) for i in range(0, len(q), 6)])
+        q += [fill_in_su()] * (n * tail_frames)
+        return np.concatenate([self.frame(q[i:i + n]) for i in range(0, len(q), n)])
 
 
 def example_messages(n, seed=1):
@@ -174,7 +183,7 @@ def main():
     import argparse
     ap = argparse.ArgumentParser(description="write the channel bits (one byte per bit) of a synthetic P channel")
     ap.add_argument("out")
-    ap.add_argument("--bitrate", type=int, default=600, choices=[600, 1200])
+    ap.add_argument("--bitrate", type=int, default=600, choices=[600, 1200, 10500])
     ap.add_argument("--messages", type=int, default=4)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--lead", type=int, default=6, help="fill-in frames before the first message: the receiver needs "
