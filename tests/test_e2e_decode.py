@@ -146,3 +146,46 @@ def test_gpu_payloads_decode_to_the_identical_acars_set(tmp_path, name):
     assert from_gpu == from_cpu
     for topic, msgs in sent.items():
         assert set(from_gpu[topic]) == expected_records(msgs), topic
+
+
+def test_restated_viterbi_round_trip_and_error_correction():
+    """oracle/viterbi_restated.c stands in for libcorrect (parity unpinned). Known-answer properties a K=7 rate-1/2 decoder
+    must have: encode -> decode is the identity (hard and soft), and isolated channel errors are corrected."""
+    import ctypes
+    lib = ctypes.CDLL(ref_decode.LIB)
+    lib.correct_convolutional_create.restype = ctypes.c_void_p
+    lib.correct_convolutional_create.argtypes = [ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p]
+    lib.correct_convolutional_encode_len.restype = ctypes.c_size_t
+    lib.correct_convolutional_encode_len.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+    lib.correct_convolutional_encode.restype = ctypes.c_size_t
+    lib.correct_convolutional_encode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    for f in (lib.correct_convolutional_decode, lib.correct_convolutional_decode_soft):
+        f.restype = ctypes.c_ssize_t
+        f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    poly = np.array([109, 79], np.uint16)
+    conv = lib.correct_convolutional_create(2, 7, poly.ctypes.data)
+    rng = np.random.default_rng(3)
+    msg = rng.integers(0, 256, 64, dtype=np.uint8)
+    nbits = lib.correct_convolutional_encode_len(conv, msg.size)
+    assert nbits == 2 * (8 * msg.size + 8)
+    enc = np.zeros((nbits + 7) // 8, np.uint8)
+    lib.correct_convolutional_encode(conv, msg.ctypes.data, msg.size, enc.ctypes.data)
+    # the same code as the transmit side of tools/aerol_frames.py
+    fr = af.PChannelFramer(600)
+    mine = fr._encode(np.unpackbits(msg))
+    assert np.array_equal(np.unpackbits(enc)[:mine.size], mine)
+    out = np.zeros(msg.size + 2, np.uint8)
+    assert lib.correct_convolutional_decode(conv, enc.ctypes.data, nbits, out.ctypes.data) > 0
+    assert np.array_equal(out[:msg.size], msg)
+    bits = np.unpackbits(enc)[:nbits].copy()
+    for pos in range(20, nbits - 40, 37):        # one flipped channel bit every 37: far apart relative to the free distance 10
+        bits[pos] ^= 1
+    hard = np.packbits(bits)
+    out[:] = 0
+    lib.correct_convolutional_decode(conv, hard.ctypes.data, nbits, out.ctypes.data)
+    assert np.array_equal(out[:msg.size], msg)
+    soft = np.where(bits > 0, 200, 55).astype(np.uint8)
+    soft[::11] = 128                              # erasures
+    out[:] = 0
+    lib.correct_convolutional_decode_soft(conv, soft.ctypes.data, nbits, out.ctypes.data)
+    assert np.array_equal(out[:msg.size], msg)
