@@ -4,6 +4,7 @@
 #include <cstring>
 #include <map>
 #include <sstream>
+#include <thread>
 #include <vector>
 
 #include "../../include/aeroddc.h"
@@ -86,7 +87,33 @@ class SyntheticSource : public IqSource {
 };
 }  // namespace
 
+bool IqSource::next(void* dst, size_t n, int sample_rate) {
+  using clock = std::chrono::steady_clock;
+  if (!started_) {
+    started_ = true;
+    if (delay_ > 0) std::this_thread::sleep_for(std::chrono::duration<double>(delay_));
+    t0_ = clock::now();
+  }
+  if (throttle_ > 0 && sample_rate > 0) {
+    // block k becomes available when an SDR running at throttle_ x real time would have finished capturing it
+    delivered_ += (double)n / (double)sample_rate;
+    std::this_thread::sleep_until(t0_ + std::chrono::duration_cast<clock::duration>(std::chrono::duration<double>(delivered_ / throttle_)));
+  }
+  return read(dst, n);
+}
+
 std::unique_ptr<IqSource> IqSource::open(const std::string& deviceStr, std::string* err) {
+  std::unique_ptr<IqSource> src = openSource(deviceStr, err);
+  if (src) {
+    auto kv = parseArgs(deviceStr);
+    if (kv.count("throttle")) src->throttle_ = atof(kv["throttle"].c_str());
+    if (kv.count("delay")) src->delay_ = atof(kv["delay"].c_str());
+    if (src->throttle_ < 0 || src->delay_ < 0) { if (err) *err = "throttle= and delay= must not be negative"; return nullptr; }
+  }
+  return src;
+}
+
+std::unique_ptr<IqSource> IqSource::openSource(const std::string& deviceStr, std::string* err) {
   auto kv = parseArgs(deviceStr);
   int fmt = AERODDC_CF32;
   if (kv.count("format")) {

@@ -198,7 +198,7 @@ void Publisher::readerThread() {
     if (aeroddc_fleet_host_slot(bank->handle(), i, &slot[i], &bytes) != AERODDC_OK) { error = aeroddc_last_error(); goto Exit; }
   while (running) {
     void* dst = slot[blocks & 1];   // the source writes straight into the pinned ring
-    if (!source->read(dst, (size_t)buflen / 2)) {
+    if (!source->next(dst, (size_t)buflen / 2, Fs)) {
       // "SoapySDR could not read stream from SDR" in the reference (publisher.cpp:269-272): end of stream
       break;
     }

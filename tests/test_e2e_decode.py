@@ -189,3 +189,54 @@ def test_restated_viterbi_round_trip_and_error_correction():
     out[:] = 0
     lib.correct_convolutional_decode_soft(conv, soft.ctypes.data, nbits, out.ctypes.data)
     assert np.array_equal(out[:msg.size], msg)
+
+
+@pytest.mark.gpu
+def test_publisher_over_zeromq_into_the_decoder(tmp_path):
+    """The literal drop-in path: aero-publish-b200 (Publisher -> CUDA bank -> vfo::transmitData -> ZmqPublisher) publishes
+    on a real ZeroMQ socket; a subscriber collects the three-frame messages exactly as aero-decode's consumer does
+    (decode.cpp:318-347) and hands the payloads to the unchanged decoder. Payload bytes must equal the CPU chain's."""
+    zmq = pytest.importorskip("zmq")
+    import socket
+    import struct
+    import time
+    sc = SCENARIOS["oqpsk10500"]
+    iq, sent = _make_capture(tmp_path, sc)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ini = tmp_path / "zmq.ini"
+    ini.write_text(open(sc["ini"]).read().replace("tcp://*:6003", "tcp://127.0.0.1:%d" % port))
+    ctx = zmq.Context.instance()
+    sub = ctx.socket(zmq.SUB)
+    for topic in sc["channels"]:
+        sub.setsockopt(zmq.SUBSCRIBE, topic.encode())
+    sub.setsockopt(zmq.RCVHWM, 100000)
+    sub.setsockopt(zmq.RCVTIMEO, 500)
+    proc = subprocess.Popen([BIN, "-d", "file=%s,format=cu8,delay=2,throttle=8" % iq, str(ini)], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    got = {}
+    try:
+        sub.connect("tcp://127.0.0.1:%d" % port)
+        quiet = 0
+        while quiet < 4:                       # until the publisher has exited and the socket stayed silent for 2 s
+            try:
+                topic, rate, payload = sub.recv_multipart()
+                got.setdefault(topic.decode(), []).append((struct.unpack("<I", rate)[0], payload))
+                quiet = 0
+            except zmq.Again:
+                quiet = quiet + 1 if proc.poll() is not None else 0
+    finally:
+        if proc.poll() is None:
+            proc.kill()
+        sub.close(0)
+    assert proc.returncode == 0, proc.stderr.read().decode()[-400:]
+    assert sorted(got) == sorted(sc["channels"])
+    cpu, zdump = tmp_path / "cpu", tmp_path / "zmq"
+    zdump.mkdir()
+    _cpu_dump(sc["ini"], iq, cpu)
+    for topic, msgs in got.items():
+        assert {r for r, _ in msgs} == {48000} and len({len(p) for _, p in msgs}) == 1
+        (zdump / (topic + ".i16")).write_bytes(b"".join(p for _, p in msgs))
+        (zdump / (topic + ".meta")).write_text("%d %d\n" % (msgs[0][0], len(msgs[0][1])))
+        assert (zdump / (topic + ".i16")).read_bytes() == (cpu / (topic + ".i16")).read_bytes(), topic
+    decoded = _decode(zdump, sc["bitrate"])
+    for topic, msgs in sent.items():
+        assert set(decoded[topic]) == expected_records(msgs), topic

@@ -159,6 +159,30 @@ def test_settings_main_vfo_limit(tmp_path):
     assert r.returncode == 1 and "more than 3 main VFOs" in r.stdout + r.stderr
 
 
+def test_source_errors_and_no_cpu_fallback(tmp_path):
+    """Device-string errors surface before any device work, like a failed SoapySDR::Device::make (publisher.cpp:27-31:
+    the constructor logs and leaves isRunning() false, main.cpp:52-55 exits 1). With a valid source and no CUDA device
+    the run must fail loudly - there is no CPU path behind Publisher."""
+    _build()
+    ini = os.path.join(DATA, "flat_2400k.ini")
+    def run(dev):
+        r = subprocess.run([BIN, "-d", dev, "--hash", ini], capture_output=True, text=True)
+        return r.returncode, r.stdout + r.stderr
+    rc, out = run("rtlsdr=0")
+    assert rc == 1 and "failed to find device" in out
+    rc, out = run("file=%s,format=cu8" % (tmp_path / "missing.cu8"))
+    assert rc == 1 and "cannot open IQ file" in out
+    (tmp_path / "x.cu8").write_bytes(b"\x80" * 1000)
+    rc, out = run("file=%s,format=cu4" % (tmp_path / "x.cu8"))
+    assert rc == 1 and "unknown IQ format" in out
+    rc, out = run("file=%s,format=cu8,throttle=-1" % (tmp_path / "x.cu8"))
+    assert rc == 1 and "must not be negative" in out
+    import torch
+    if not torch.cuda.is_available():
+        rc, out = run("synthetic=1,format=cu8,blocks=1")
+        assert rc == 1 and "CUDA" in out.upper()
+
+
 def test_zmq_wire_format_over_a_real_socket():
     """ZmqPublisher through libzmq (dlopen) to a pyzmq SUB socket: three frames - 5 topic bytes, uint32 LE
     rate, payload - as aero-decode's consumer expects (zmqpublisher.cpp:61-73, decode/decode.cpp:283-366)."""
