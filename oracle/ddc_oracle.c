@@ -142,8 +142,9 @@ void ddc_unpack(int fmt, const void *raw, long long n_complex, float *out) {
 
 /* Publisher::demodData's optional DC removal (publisher.cpp:292-296), in place on interleaved float I,Q:
  *   avept = avept * (1.0f - 0.000001f) + 0.000001f * curr;  curr -= avept;   (std::complex<float>: per rail)
- * state[2] is the running average (function-static in the reference). PARITY UNPINNED for this function:
- * publisher.cpp cannot be compiled here (Qt, SoapySDR), so it is a restatement checked by reading only. */
+ * state[2] is the running average (function-static in the reference). Pinned: the unmodified publisher.cpp
+ * (oracle/_ref/ref_publish) with --enable-dcc yields byte-identical payloads to this function followed by the
+ * chain (tests/test_reference_publisher.py). */
 void ddc_dc_correct(float *iq, long long n_complex, float *state) {
   const float k = 1.0f - 0.000001f, c = 0.000001f;
   for (long long i = 0; i < n_complex; i++)

@@ -1,0 +1,1 @@
+#include "qt_publisher_shim.h"

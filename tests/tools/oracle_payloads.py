@@ -4,7 +4,7 @@ IQ file with the VFO tree of a settings file and write per-topic payload dumps i
 `aero-publish-b200 --dump DIR`, so that CPU and GPU payloads can be compared byte for byte
 (`cmp cpu/VFO01.i16 gpu/VFO01.i16`) and replayed into an unchanged aero-decode (tools/replay_payloads.py).
 
-    tests/tools/oracle_payloads.py settings.ini capture.cu8 cu8 cpu_dump/
+    tests/tools/oracle_payloads.py settings.ini capture.cu8 cu8 cpu_dump/ [dcc]
 """
 import json
 import os
@@ -15,7 +15,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
-from oracle_bind import Oracle, unpack  # noqa: E402
+from oracle_bind import Oracle, dc_correct, unpack  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(HERE))
 BIN = os.path.join(ROOT, "aero-cli_b200", "aero-publish-b200")
@@ -24,6 +24,8 @@ FMT = {"cu8": (0, np.uint8), "cs16": (1, np.int16), "cf32": (2, np.float32)}
 
 def main():
     ini, iq, fmt, out = sys.argv[1:5]
+    dcc = len(sys.argv) > 5 and sys.argv[5] in ("dcc", "1")
+    dc_state = np.zeros(2, np.float32)
     os.makedirs(out, exist_ok=True)
     plan = json.loads(subprocess.run([BIN, "--plan", ini], check=True, capture_output=True, text=True).stdout)
     Fs, B = plan["sample_rate"], plan["block"]
@@ -46,6 +48,8 @@ def main():
             if raw.size < 2 * B:
                 break
             x = raw if code == 2 else unpack(code, raw)
+            if dcc:      # Publisher::demodData's DC removal ahead of every VFO (publisher.cpp:292-296)
+                x = dc_correct(np.array(x, np.float32), dc_state)
             mid = []
             for m in mains:
                 m.process(x)
