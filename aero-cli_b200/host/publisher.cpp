@@ -64,126 +64,131 @@ bool Publisher::parseOnly(const std::string& settingsPath, Publisher** out, std:
   return ok;
 }
 
+// ---- settings-file rules (Publisher::loadSettings, publisher.cpp:55-227), one function per rule -----------------------
+namespace {
+
+// publisher.cpp:93-100: four blocks per second of interleaved floats, five when a quarter is not a multiple of 512
+struct BlockSplit { int parts, floats; };
+BlockSplit splitBlocks(int fs) {
+  const long long twice = 2LL * fs;
+  if ((int)(twice / 4) % 512 > 0) return {5, (int)(twice / 5)};
+  return {4, (int)(twice / 4)};
+}
+
+// publisher.cpp:140-141: integer ratio, log2 truncated; a ratio of 1 is no decimation
+int mainDecimation(int fs, int out_rate) {
+  const int ratio = fs / out_rate;
+  return ratio == 1 ? 0 : (int)std::log2(ratio);
+}
+
+// publisher.cpp:164-176: an explicit out_rate wins, else the channel's bit rate picks the audio rate
+int audioRate(int out_rate, int data_rate) {
+  if (out_rate != 0 || data_rate <= 0) return out_rate;
+  if (data_rate == 600) return 12000;
+  if (data_rate == 1200) return 24000;
+  return 48000;
+}
+
+// publisher.cpp:198-210: a parent at 5 x or 6 x 48 kHz uses the late /5 or /6 stage; otherwise plain halvings
+struct Chain { int halvings, late; };
+Chain subChain(int fs, int parent_rate, int out_rate) {
+  const int k = parent_rate / 48000;
+  if (k == 5 || k == 6) return {(int)std::log2(parent_rate / (k * out_rate)), k};
+  return {(int)std::log2(fs / out_rate) - (int)std::log2(fs / parent_rate), 0};
+}
+
+}  // namespace
+
+// publisher.cpp:183-193: the first main VFO that only feeds sub-VFOs and lies within ONE output rate (not half) wins
+int Publisher::matchMainVfo(int vfo_freq) const {
+  for (size_t a = 0; a < VFOmain.size(); ++a) {
+    vfo* m = VFOmain[a];   // the getters are non-const like the reference's (vfo.h:31-38)
+    const int offset = std::abs((center_frequency - m->getMixerFreq()) - vfo_freq);
+    if (offset < m->getOutRate() && !m->getDemodUSB()) return (int)a;
+  }
+  return -1;
+}
+
 bool Publisher::loadSettings(const std::string& settingsPath) {
-  aero::IniSettings settings;
-  if (!settings.load(settingsPath)) {
+  aero::IniSettings ini;
+  if (!ini.load(settingsPath)) {
     error = "Provided settings file path either doesn't exist or isn't a file: " + settingsPath;
     return false;
   }
-  Fs = settings.toInt("sample_rate");
+  Fs = ini.toInt("sample_rate");
   if (Fs == 0) { error = "Provided sample rate in settings file either doesn't exist or isn't an integer"; return false; }
-  bool valid = false;
-  for (int r : validSampleRates) valid = valid || r == Fs;
-  if (!valid) { error = "Provided sample rate is not supported: " + std::to_string(Fs); return false; }
-
-  center_frequency = settings.toInt("center_frequency");
-  tuner_idx = settings.toInt("auto_start_tuner_idx");
-  enableBiast = enableBiast || (settings.toInt("auto_start_biast") == 1);
-  const int gain = settings.toInt("tuner_gain");
-  const int remote_gain_idx = settings.toInt("remote_rtl_gain_idx");
-  const int mix_offset = settings.toInt("mix_offset");
-
-  // usually 4 buffers per Fs but in some cases 5 due to multiple of 512 (publisher.cpp:93-100)
-  int bufsplit = 4;
-  if (double((int((2 * (long long)Fs) / 4)) % 512) > 0) {
-    buflen = int((2 * (long long)Fs) / 5);
-    bufsplit = 5;
-  } else {
-    buflen = int((2 * (long long)Fs) / 4);
+  if (std::find(validSampleRates.begin(), validSampleRates.end(), Fs) == validSampleRates.end()) {
+    error = "Provided sample rate is not supported: " + std::to_string(Fs);
+    return false;
   }
-  if (gain > 0) tuner_gain = gain;
-  if (remote_gain_idx > 0) tuner_gain_idx = remote_gain_idx;
-  const std::string zmq_address = settings.value("zmq_address");
-  enableDcc = enableDcc || settings.value("correct_dc_bias") == "1";
+  center_frequency = ini.toInt("center_frequency");
+  tuner_idx = ini.toInt("auto_start_tuner_idx");
+  if (ini.toInt("auto_start_biast") == 1) enableBiast = true;
+  if (ini.toInt("tuner_gain") > 0) tuner_gain = ini.toInt("tuner_gain");
+  if (ini.toInt("remote_rtl_gain_idx") > 0) tuner_gain_idx = ini.toInt("remote_rtl_gain_idx");
+  if (ini.value("correct_dc_bias") == "1") enableDcc = true;
+  const int mix_offset = ini.toInt("mix_offset");
+  const std::string pub_address = ini.value("zmq_address");
+  const BlockSplit split = splitBlocks(Fs);
+  buflen = split.floats;
 
-  const int msize = settings.beginReadArray("main_vfos");
-  if (msize > 3) { error = "more than 3 main VFOs (VFOsub[3], publisher.h:50)"; return false; }
-  for (int i = 0; i < msize; ++i) {   // publisher.cpp:118-148
-    settings.setArrayIndex(i);
-    vfo* pVFO = new vfo();
-    const int vfo_freq = settings.toInt("frequency");
-    const int vfo_out_rate = settings.toInt("out_rate");
-    const std::string output_connect = settings.value("zmq_address");
-    const std::string out_topic = settings.value("zmq_topic");
-    const int compscale = settings.toInt("compress_scale");
-    if (vfo_out_rate <= 0) { delete pVFO; error = "main VFO without out_rate"; return false; }
-    if (compscale > 0) pVFO->setScaleComp(compscale);
-    if (output_connect != "" && out_topic != "") {
-      pVFO->setZmqAddress(output_connect);
-      pVFO->setZmqTopic(out_topic);
+  // [main_vfos] (publisher.cpp:118-148): mix + decimate only; their stage-D stream feeds the sub-VFOs
+  const int n_main = ini.beginReadArray("main_vfos");
+  if (n_main > 3) { error = "more than 3 main VFOs (VFOsub[3], publisher.h:50)"; return false; }
+  for (int i = 0; i < n_main; ++i) {
+    ini.setArrayIndex(i);
+    const int rate = ini.toInt("out_rate");
+    if (rate <= 0) { error = "main VFO without out_rate"; return false; }
+    vfo* m = new vfo();
+    if (ini.toInt("compress_scale") > 0) m->setScaleComp(ini.toInt("compress_scale"));
+    if (!ini.value("zmq_address").empty() && !ini.value("zmq_topic").empty()) {
+      m->setZmqAddress(ini.value("zmq_address"));
+      m->setZmqTopic(ini.value("zmq_topic"));
     }
-    pVFO->setFs(Fs);
-    pVFO->setDecimationCount(Fs / vfo_out_rate == 1 ? 0 : int(log2(Fs / vfo_out_rate)));
-    pVFO->setMixerFreq(center_frequency - vfo_freq);
-    pVFO->setDemodUSB(false);
-    pVFO->setCompressonStyle(1);
-    pVFO->init(buflen / 2, false);
-    pVFO->setVFOs(&VFOsub[i]);
-    VFOmain.push_back(pVFO);
+    m->setFs(Fs);
+    m->setDecimationCount(mainDecimation(Fs, rate));
+    m->setMixerFreq(center_frequency - ini.toInt("frequency"));
+    m->setDemodUSB(false);
+    m->setCompressonStyle(1);
+    m->init(buflen / 2, false);
+    m->setVFOs(&VFOsub[i]);
+    VFOmain.push_back(m);
   }
-  settings.endArray();
+  ini.endArray();
 
-  const int size = settings.beginReadArray("vfos");
-  nVFO = size;
-  for (int i = 0; i < size; ++i) {   // publisher.cpp:156-222
-    settings.setArrayIndex(i);
-    vfo* pVFO = new vfo();
-    const int vfo_freq = settings.toInt("frequency") + mix_offset;
-    const int data_rate = settings.toInt("data_rate");
-    int out_rate = settings.toInt("out_rate");
-    if (out_rate == 0 && data_rate > 0) {
-      switch (data_rate) {
-        case 600: out_rate = 12000; break;
-        case 1200: out_rate = 24000; break;
-        default: out_rate = 48000; break;
-      }
-    }
-    if (out_rate <= 0) { delete pVFO; error = "VFO " + std::to_string(i + 1) + " has neither out_rate nor data_rate"; return false; }
-    const int filterbw = settings.toInt("filter_bandwidth");
-    int main_vfo_freq = 0;
-    int main_vfo_out_rate = Fs;
-    int main_idx = -1;
-    for (size_t a = 0; a < VFOmain.size(); a++) {   // first main VFO within one output rate wins (not half)
-      const int diff = std::abs((center_frequency - VFOmain[a]->getMixerFreq()) - vfo_freq);
-      if (diff < VFOmain[a]->getOutRate() && !VFOmain[a]->getDemodUSB()) {
-        main_idx = (int)a;
-        main_vfo_freq = VFOmain[a]->getMixerFreq();
-        main_vfo_out_rate = VFOmain[a]->getOutRate();
-        break;
-      }
-    }
-    pVFO->setZmqTopic(settings.value("topic"));
-    pVFO->setZmqAddress(zmq_address);
-    int lateDecimate = 0;
-    if ((main_vfo_out_rate / 48000) == 5) {
-      pVFO->setDecimationCount(int(log2(main_vfo_out_rate / (5 * out_rate))));
-      lateDecimate = 5;
-    } else if ((main_vfo_out_rate / 48000) == 6) {
-      pVFO->setDecimationCount(int(log2(main_vfo_out_rate / (6 * out_rate))));
-      lateDecimate = 6;
-    } else {
-      pVFO->setDecimationCount(int(log2(Fs / out_rate)) - int(log2(Fs / main_vfo_out_rate)));
-    }
-    pVFO->setFilterBandwidth(filterbw);
-    pVFO->setGain((float)settings.toFloat("gain") / 100);
-    pVFO->setMixerFreq((center_frequency - main_vfo_freq) - vfo_freq);
-    pVFO->setFs(main_vfo_out_rate);
-    pVFO->setCompressonStyle(1);
-    pVFO->init(main_vfo_out_rate / bufsplit, true, lateDecimate);
-    if (main_idx >= 0) {
-      VFOsub[main_idx].push_back(pVFO);
-    } else if (VFOmain.empty()) {
-      // The reference parks such a VFO in VFOsub[0] and never processes it (demodData only walks the main
-      // VFOs, publisher.cpp:301-305). Here a settings file without [main_vfos] describes a flat bank on the raw stream.
-      VFOflat.push_back(pVFO);
-    } else {
-      // with main VFOs present the reference would feed this VFO a stream of the wrong rate (publisher.cpp:219)
-      delete pVFO;
-      error = "VFO " + std::to_string(i + 1) + " matches no main VFO";
+  // [vfos] (publisher.cpp:156-222): USB-demodulating leaves, each behind the main VFO it matches
+  nVFO = ini.beginReadArray("vfos");
+  for (int i = 0; i < nVFO; ++i) {
+    ini.setArrayIndex(i);
+    const std::string label = "VFO " + std::to_string(i + 1);
+    const int vfo_freq = ini.toInt("frequency") + mix_offset;
+    const int out_rate = audioRate(ini.toInt("out_rate"), ini.toInt("data_rate"));
+    if (out_rate <= 0) { error = label + " has neither out_rate nor data_rate"; return false; }
+    const int parent = matchMainVfo(vfo_freq);
+    if (parent < 0 && !VFOmain.empty()) {
+      // the reference would park it in VFOsub[0] and feed it a stream of the wrong rate (publisher.cpp:219)
+      error = label + " matches no main VFO";
       return false;
     }
+    const int parent_mixer = parent < 0 ? 0 : (int)VFOmain[parent]->getMixerFreq();
+    const int parent_rate = parent < 0 ? Fs : VFOmain[parent]->getOutRate();
+    const Chain chain = subChain(Fs, parent_rate, out_rate);
+    vfo* v = new vfo();
+    v->setZmqTopic(ini.value("topic"));
+    v->setZmqAddress(pub_address);
+    v->setDecimationCount(chain.halvings);
+    v->setFilterBandwidth(ini.toInt("filter_bandwidth"));
+    v->setGain((float)ini.toFloat("gain") / 100);
+    v->setMixerFreq((center_frequency - parent_mixer) - vfo_freq);
+    v->setFs(parent_rate);
+    v->setCompressonStyle(1);
+    v->init(parent_rate / split.parts, true, chain.late);
+    // Without [main_vfos] the reference builds these VFOs but never runs them (demodData walks the main VFOs only,
+    // publisher.cpp:301-305); here such a file describes a flat bank on the raw stream.
+    if (parent >= 0) VFOsub[parent].push_back(v);
+    else VFOflat.push_back(v);
   }
-  settings.endArray();
+  ini.endArray();
   return true;
 }
 

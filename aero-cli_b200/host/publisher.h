@@ -46,6 +46,7 @@ class Publisher {
  private:
   Publisher() {}
   bool loadSettings(const std::string& settingsPath);
+  int matchMainVfo(int vfo_freq) const;   // index of the main VFO a [vfos] entry hangs under, or -1
   void readerThread();
   void demodData(void* block);
 
