@@ -80,7 +80,6 @@ struct aeroddc_fleet {
   std::vector<cudaStream_t> streams;            // per device: carries the broadcast
   std::vector<unsigned char*> d_in[2];          // per device raw block, two parities
   std::vector<cudaEvent_t> ev_ready[2];         // per device: block of parity p has arrived
-  std::vector<cudaEvent_t> ev_free[2];          // per device: the bank has finished reading parity p
   void* h_slot[2] = {nullptr, nullptr};
   long long submitted = 0, done = 0;
 };
@@ -159,14 +158,13 @@ int aeroddc_fleet_finalize(aeroddc_fleet* f) {
     FNC(nccl().CommInitAll(f->comms.data(), nd, f->devices.data()));
   }
   f->streams.resize(nd);
-  for (int p = 0; p < 2; ++p) { f->d_in[p].resize(nd); f->ev_ready[p].resize(nd); f->ev_free[p].resize(nd); }
+  for (int p = 0; p < 2; ++p) { f->d_in[p].resize(nd); f->ev_ready[p].resize(nd); }
   for (int i = 0; i < nd; ++i) {
     FCU(cudaSetDevice(f->devices[i]));
     FCU(cudaStreamCreateWithFlags(&f->streams[i], cudaStreamNonBlocking));
     for (int p = 0; p < 2; ++p) {
       FCU(cudaMalloc((void**)&f->d_in[p][i], f->in_bytes));
       FCU(cudaEventCreateWithFlags(&f->ev_ready[p][i], cudaEventDisableTiming));
-      FCU(cudaEventCreateWithFlags(&f->ev_free[p][i], cudaEventDisableTiming));
     }
   }
   f->finalized = true;
@@ -193,7 +191,8 @@ int aeroddc_fleet_submit(aeroddc_fleet* f, const void* host_iq, size_t n_complex
     memcpy(f->h_slot[p], host_iq, f->in_bytes);
     src = f->h_slot[p];
   }
-  // the buffers of parity p were last read by the block submitted two calls ago, which wait() has retired
+  // the buffers of parity p were last read by the block submitted two calls ago; the in-flight limit above means
+  // wait() has retired it (payload copied out, hence kernels done), so no event is needed before overwriting them
   FCU(cudaSetDevice(f->devices[0]));
   FCU(cudaMemcpyAsync(f->d_in[p][0], src, f->in_bytes, cudaMemcpyHostToDevice, f->streams[0]));
   if (nd > 1) {
@@ -297,7 +296,6 @@ void aeroddc_fleet_destroy(aeroddc_fleet* f) {
     for (int p = 0; p < 2; ++p) {
       if (i < f->d_in[p].size()) cudaFree(f->d_in[p][i]);
       if (i < f->ev_ready[p].size() && f->ev_ready[p][i]) cudaEventDestroy(f->ev_ready[p][i]);
-      if (i < f->ev_free[p].size() && f->ev_free[p][i]) cudaEventDestroy(f->ev_free[p][i]);
     }
     if (f->streams[i]) cudaStreamDestroy(f->streams[i]);
   }
