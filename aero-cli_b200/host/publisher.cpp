@@ -196,33 +196,41 @@ void Publisher::run() { mainReader = std::thread([this] { readerThread(); }); }
 void Publisher::wait() { if (mainReader.joinable()) mainReader.join(); }
 
 void Publisher::readerThread() {
+  // The reference reads a block and runs every VFO on it before reading the next (publisher.cpp:266-276). Here the
+  // two halves of the pinned host ring alternate: while the GPUs work on block k (async H2D, kernels, payload D2H)
+  // the source fills the other half with block k+1, and block k+1 is submitted before block k is published.
   void* slot[2] = {nullptr, nullptr};
   size_t bytes = 0;
+  const size_t n = (size_t)buflen / 2;
   if (!running) goto Exit;
   for (int i = 0; i < 2; ++i)
     if (aeroddc_fleet_host_slot(bank->handle(), i, &slot[i], &bytes) != AERODDC_OK) { error = aeroddc_last_error(); goto Exit; }
-  while (running) {
-    void* dst = slot[blocks & 1];   // the source writes straight into the pinned ring
-    if (!source->next(dst, (size_t)buflen / 2, Fs)) {
-      // "SoapySDR could not read stream from SDR" in the reference (publisher.cpp:269-272): end of stream
-      break;
+  try {
+    // a failed read is "SoapySDR could not read stream from SDR" in the reference (publisher.cpp:269-272): end of stream
+    bool have = source->next(slot[0], n, Fs);
+    if (have) demodData(slot[0]);
+    for (long long k = 0; have; ++k) {
+      const bool more = running && source->next(slot[(k + 1) & 1], n, Fs);
+      bank->wait();                                  // block k; its payloads stay valid until the next wait()
+      if (more) demodData(slot[(k + 1) & 1]);
+      transmitData();
+      have = more;
     }
-    try {
-      demodData(dst);
-    } catch (const std::exception& e) {
-      error = e.what();
-      CRIT("%s", e.what());
-      break;
-    }
+  } catch (const std::exception& e) {
+    error = e.what();
+    CRIT("%s", e.what());
   }
 Exit:
   running = false;
   if (completed) completed();
 }
 
-void Publisher::demodData(void* block) {
-  bank->process(block, (size_t)buflen / 2);       // every main VFO, sub-VFO and flat VFO in one GPU pass
-  for (vfo* m : VFOmain) m->transmitData();       // publisher.cpp:301-305 + vfo::transmitData
+// hands one raw block to every main VFO, sub-VFO and flat VFO: one asynchronous GPU pass (publisher.cpp:285-306)
+void Publisher::demodData(void* block) { bank->submit(block, (size_t)buflen / 2); }
+
+// one ZeroMQ message per publishing VFO for the block that wait() just retired (publisher.cpp:301-305 -> vfo::transmitData)
+void Publisher::transmitData() {
+  for (vfo* m : VFOmain) m->transmitData();
   for (vfo* f : VFOflat) f->transmitData();
   ++blocks;
 }

@@ -49,6 +49,7 @@ class Publisher {
   int matchMainVfo(int vfo_freq) const;   // index of the main VFO a [vfos] entry hangs under, or -1
   void readerThread();
   void demodData(void* block);
+  void transmitData();
 
   // the reference accepts {288000, 1536000, 1920000} (publisher.h:32); 2.4 and 61.44 MS/s are the
   // BASELINE.json benchmark rates the GPU bank adds

@@ -20,6 +20,13 @@ void DdcBank::process(const void* host_iq, size_t n_complex) {
   if (aeroddc_fleet_process(bank_, host_iq, n_complex) != AERODDC_OK)
     throw std::runtime_error(std::string("aeroddc_fleet_process: ") + aeroddc_last_error());
 }
+void DdcBank::submit(const void* host_iq, size_t n_complex) {
+  if (aeroddc_fleet_submit(bank_, host_iq, n_complex) != AERODDC_OK)
+    throw std::runtime_error(std::string("aeroddc_fleet_submit: ") + aeroddc_last_error());
+}
+void DdcBank::wait() {
+  if (aeroddc_fleet_wait(bank_) != AERODDC_OK) throw std::runtime_error(std::string("aeroddc_fleet_wait: ") + aeroddc_last_error());
+}
 
 }  // namespace aero
 

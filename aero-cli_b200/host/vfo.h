@@ -36,7 +36,9 @@ class DdcBank {
   int format() const { return format_; }
   bool finalized() const { return finalized_; }
   void finalize();                                  // throws std::runtime_error with aeroddc_last_error()
-  void process(const void* host_iq, size_t n_complex);
+  void process(const void* host_iq, size_t n_complex);   // submit + wait
+  void submit(const void* host_iq, size_t n_complex);    // async H2D + kernels + payload D2H; at most two blocks in flight
+  void wait();                                           // oldest block in flight; its payloads stay valid until the next wait()
  private:
   aeroddc_fleet* bank_ = nullptr;
   int block_len_, format_;
