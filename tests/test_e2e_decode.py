@@ -240,3 +240,42 @@ def test_publisher_over_zeromq_into_the_decoder(tmp_path):
     decoded = _decode(zdump, sc["bitrate"])
     for topic, msgs in sent.items():
         assert set(decoded[topic]) == expected_records(msgs), topic
+
+
+def test_frame_generator_pieces():
+    """Internal invariants of tools/aerol_frames.py that do not need the decoder: CRC residue, parity, interleaver bijection,
+    scrambler period, frame lengths, ISU segmentation limits."""
+    su = af.signal_unit(range(10))
+    assert len(su) == 12 and af.crc16(su[:10]) == su[10] | (su[11] << 8)
+    assert af.crc16(b"123456789") == 0x906E                       # CRC-16/X-25 check value: the variant AeroLcrc16 computes
+    assert all(bin(af.odd_parity(c)).count("1") % 2 == 1 for c in range(128))
+    for rate, cols, nbits, nsu in ((600, 6, 1200, 6), (1200, 9, 1200, 6), (10500, 78, 5250, 26)):
+        fr = af.PChannelFramer(rate)
+        assert sorted(fr.tx_pos) == list(range(64 * cols))        # the interleaver is a permutation of one block
+        assert fr.frame([af.fill_in_su()] * nsu).size == nbits == fr.frame_bits
+    seq = af.scrambler_sequence(2 * 32767 + 10)
+    assert np.array_equal(seq[:32767 + 10], seq[32767:2 * 32767 + 10]) and 0 < seq[:32767].sum() < 32767   # x^15 + x^14 + 1: maximal length
+    ud = af.acars_user_data(".N123AB", "H1", "X" * 230)
+    sus = af.isu_signal_units(0x123456, 0x90, 3, 4, ud)
+    assert len(sus) == 1 + (len(ud) - 2 + 7) // 8 and sus[0][0] == 0x71 and sus[0][6] == len(sus) - 1
+    assert [s[0] & 0x3F for s in sus[1:]] == list(range(len(sus) - 2, -1, -1))     # SSU sequence numbers count down to 0
+    with pytest.raises(AssertionError):
+        af.isu_signal_units(1, 2, 3, 4, bytes(2 + 8 * 64))        # more than 63 SSUs do not fit the 6-bit count
+
+
+def test_long_and_multi_block_messages_through_the_reference_decoder():
+    """A 210-character text (28 SSUs, spanning five 600 bit/s frames) and an ETB-terminated first block of a multi-block
+    message: the reference reassembles the first and reports the second as a fragment with 'more to come'."""
+    long_text = " ".join("WPT%02d N%04d W%05d" % (i, 4000 + 7 * i, 7000 + 13 * i) for i in range(11))[:210]
+    sus = af.isu_signal_units(0xABCDEF, 0x85, 5, 6, af.acars_user_data(".D-AIXY", "H1", long_text))
+    sus += af.isu_signal_units(0x400A0B, 0x85, 6, 7, af.acars_user_data(".G-XLEA", "B6", "PART ONE OF TWO", more=True))
+    dec = ref_decode.RefDecoder(600)
+    soft = af.PChannelFramer(600).stream(sus).astype(np.int16) * 255
+    for i in range(0, soft.size, 12):
+        dec.feed_softbits(soft[i:i + 12])
+    got = dec.records()
+    dec.close()
+    assert "FRAGMENT|AES=ABCDEF|GES=85|QNO=05|REFNO=06|MODE=32|TAK=15|BI=31|DL=0|MORE=0|NONACARS=0|LABEL=H1|REG=.D-AIXY|TEXT=" + long_text in got
+    assert "ACARS|AES=ABCDEF|GES=85|QNO=05|REFNO=06|MODE=32|TAK=15|BI=31|DL=0|MORE=0|NONACARS=0|LABEL=H1|REG=D-AIXY|TEXT=" + long_text in got
+    assert "FRAGMENT|AES=400A0B|GES=85|QNO=06|REFNO=07|MODE=32|TAK=15|BI=31|DL=0|MORE=1|NONACARS=0|LABEL=B6|REG=.G-XLEA|TEXT=PART ONE OF TWO" in got
+    assert not any(r.startswith("ACARS|AES=400A0B") for r in got)      # the defragmenter waits for the closing block
