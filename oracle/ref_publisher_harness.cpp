@@ -12,6 +12,11 @@
 // It pins what the vfo-level oracle cannot: Publisher::loadSettings' arithmetic and matching rules on the real
 // code, the main -> sub VFO tree exactly as the reference builds it, and the DC-correction recurrence.
 //
+// A second build of this file, -DAERODDC_GPU_VFO (oracle/_ref/ref_publish_gpuvfo), puts the PRODUCT's `vfo` class
+// (aero-cli_b200/host/vfo.{h,cpp}, the CUDA bank behind it) under the same unmodified publisher.cpp instead of the
+// reference's vfo.cpp: the reference's Publisher then drives the GPU through nothing but the class surface SURVEY.md
+// section 8b lists - the drop-in claim at link level. Payloads are captured through ZmqPublisher::setSink.
+//
 //   ref_publish <settings.ini> <iq file> <cu8|cs16|cf32> <dcc 0|1> <out dir>
 // writes <out dir>/<TOPIC>.i16 + <TOPIC>.meta ("rate bytes_per_message"), the layout of `aero-publish-b200 --dump`,
 // and prints one JSON line with the VFO tree the reference built.
@@ -21,7 +26,9 @@
 
 #include <SoapySDR/Device.hpp>
 
+#ifndef AERODDC_GPU_VFO
 #include "zmq.h"
+#endif
 
 #define private public   // the harness reads the VFO tree the constructor built and calls the reader loop's owner
 #include "publisher.h"
@@ -47,6 +54,17 @@ uint32_t g_cur_rate = 0;
 int g_token;
 }  // namespace
 
+static void keep_message(const std::string& topic, uint32_t rate, const void* buf, size_t len) {
+  std::string key(topic.c_str());   // a short topic is padded with NULs on the wire (zmqpublisher.cpp:69)
+  if (!g_topics.count(key)) g_order.push_back(key);
+  Topic& t = g_topics[key];
+  t.payload.append((const char*)buf, len);
+  t.rate = rate;
+  t.msg_bytes = (uint32_t)len;
+  t.msgs++;
+}
+
+#ifndef AERODDC_GPU_VFO
 extern "C" {
 void* zmq_ctx_new(void) { return &g_token; }
 void* zmq_socket(void*, int) { return &g_token; }
@@ -56,19 +74,12 @@ int zmq_connect(void*, const char*) { return 0; }
 int zmq_send(void*, const void* buf, size_t len, int flags) {
   if (g_frame == 0) g_cur_topic.assign((const char*)buf, len);
   else if (g_frame == 1) { g_cur_rate = 0; std::memcpy(&g_cur_rate, buf, len < 4 ? len : 4); }
-  else {
-    std::string key(g_cur_topic.c_str());   // a short topic is padded with NULs on the wire (zmqpublisher.cpp:69)
-    if (!g_topics.count(key)) g_order.push_back(key);
-    Topic& t = g_topics[key];
-    t.payload.append((const char*)buf, len);
-    t.rate = g_cur_rate;
-    t.msg_bytes = (uint32_t)len;
-    t.msgs++;
-  }
+  else keep_message(g_cur_topic, g_cur_rate, buf, len);
   g_frame = (flags & ZMQ_SNDMORE) ? g_frame + 1 : 0;
   return (int)len;
 }
 }
+#endif
 
 // ---- SoapySDR: IQ-file device ----------------------------------------------------------------------------------------
 namespace {
@@ -142,6 +153,9 @@ int main(int argc, char** argv) {
   }
   const std::string ini = argv[1], iq = argv[2], fmt = argv[3], out = argv[5];
   const bool dcc = atoi(argv[4]) != 0;
+#ifdef AERODDC_GPU_VFO
+  ZmqPublisher::setSink([](const std::string& topic5, uint32_t rate, const unsigned char* p, uint32_t n) { keep_message(topic5, rate, p, n); });
+#endif
   Publisher* pub = new Publisher(QString(("file=" + iq + ",format=" + fmt).c_str()), false, dcc, QString(ini.c_str()));
   if (!pub->isRunning()) {
     printf("{\"error\": \"reference Publisher did not start (settings or source rejected)\"}\n");

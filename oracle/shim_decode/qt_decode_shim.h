@@ -293,6 +293,10 @@ public:
   QByteArray toLatin1() const { return QByteArray(d); }
   QByteArray toUtf8() const { return QByteArray(d); }
   QByteArray toLocal8Bit() const { return QByteArray(d); }
+#ifdef AERODDC_QSTRING_IS_STD_STRING
+  // only for the build that puts the product's `vfo` class (std::string setters) under the reference's publisher.cpp
+  operator std::string() const { return d; }
+#endif
   std::string toStdString() const { return d; }
   static QString fromStdString(const std::string& s) { return QString(s); }
   static QString fromLatin1(const char* s, int n = -1) { return n < 0 ? QString(s) : QString(std::string(s, (size_t)n)); }

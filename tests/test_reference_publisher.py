@@ -132,3 +132,46 @@ def test_product_equals_the_reference_publisher(tmp_path, name, fmt, dcc):
     assert names == sorted(os.listdir(gpu)) and names
     for f in names:
         assert filecmp.cmp(tmp_path / "ref" / f, gpu / f, shallow=False), f
+
+
+GPUVFO = os.path.join(ROOT, "oracle", "_ref", "ref_publish_gpuvfo")
+
+
+@pytest.mark.skipif(not os.path.exists(GPUVFO), reason="oracle/_ref/ref_publish_gpuvfo not built (make -C oracle refpublish_gpuvfo)")
+def test_reference_publisher_on_the_product_vfo_class_has_no_cpu_path(tmp_path):
+    """oracle/_ref/ref_publish_gpuvfo = the reference's unmodified publisher.cpp linked against the PRODUCT's vfo class.
+    Without a CUDA device the first vfo::process must fail loudly (no CPU fallback behind the class surface)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present; the GPU variant of this test covers the path")
+    ini = os.path.join(DATA, "e2e_288k.ini")
+    iq = tmp_path / "c.cu8"
+    _capture(iq, 288000, "cu8", 1)
+    (tmp_path / "out").mkdir()
+    r = subprocess.run([GPUVFO, ini, str(iq), "cu8", "0", str(tmp_path / "out")], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+    assert not os.listdir(tmp_path / "out")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(GPUVFO), reason="oracle/_ref/ref_publish_gpuvfo not built (make -C oracle refpublish_gpuvfo)")
+@pytest.mark.skipif(not os.environ.get("AERODDC_RUN_UNVERIFIED"),
+                    reason="built after round 1's GPU minutes were spent: not yet run on hardware, enable with AERODDC_RUN_UNVERIFIED=1")
+@pytest.mark.parametrize("name,fmt,dcc", [("e2e_288k.ini", "cu8", True), ("two_mains_1920k.ini", "cf32", False)])
+def test_reference_publisher_source_drives_the_product_vfo_class(tmp_path, name, fmt, dcc):
+    """Drop-in at link level: the reference's own Publisher (settings, reader loop, DC correction - all its code) calls
+    setFs / setDecimationCount / ... / init / process on the product's vfo objects, one private GPU bank per main VFO.
+    The payloads must equal those of the all-reference build."""
+    ini = os.path.join(DATA, name)
+    iq = tmp_path / ("c." + fmt)
+    _capture(iq, _fs(ini), fmt, 4, dc=0.08 if dcc else 0.0)
+    rc, ref = _ref_run(ini, iq, fmt, dcc, tmp_path / "ref")
+    assert rc == 0
+    gpu = tmp_path / "gpu"
+    gpu.mkdir()
+    r = subprocess.run([GPUVFO, ini, str(iq), fmt, "1" if dcc else "0", str(gpu)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-400:]
+    names = sorted(os.listdir(tmp_path / "ref"))
+    assert names == sorted(os.listdir(gpu)) and names
+    for f in names:
+        assert filecmp.cmp(tmp_path / "ref" / f, gpu / f, shallow=False), f
