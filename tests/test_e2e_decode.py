@@ -279,3 +279,48 @@ def test_long_and_multi_block_messages_through_the_reference_decoder():
     assert "ACARS|AES=ABCDEF|GES=85|QNO=05|REFNO=06|MODE=32|TAK=15|BI=31|DL=0|MORE=0|NONACARS=0|LABEL=H1|REG=D-AIXY|TEXT=" + long_text in got
     assert "FRAGMENT|AES=400A0B|GES=85|QNO=06|REFNO=07|MODE=32|TAK=15|BI=31|DL=0|MORE=1|NONACARS=0|LABEL=B6|REG=.G-XLEA|TEXT=PART ONE OF TWO" in got
     assert not any(r.startswith("ACARS|AES=400A0B") for r in got)      # the defragmenter waits for the closing block
+
+
+def test_replayed_cpu_payloads_decode_over_zeromq(tmp_path):
+    """The CPU-only twin of test_publisher_over_zeromq_into_the_decoder: tools/replay_payloads.py puts the CPU chain's dump on
+    a real ZeroMQ socket in the reference's wire format; what a subscriber receives decodes to the sent messages."""
+    zmq = pytest.importorskip("zmq")
+    import socket
+    import struct
+    sc = SCENARIOS["oqpsk10500"]
+    iq, sent = _make_capture(tmp_path, sc)
+    cpu = tmp_path / "cpu"
+    _cpu_dump(sc["ini"], iq, cpu)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = zmq.Context.instance()
+    sub = ctx.socket(zmq.SUB)
+    sub.setsockopt(zmq.SUBSCRIBE, b"")
+    sub.setsockopt(zmq.RCVHWM, 100000)
+    sub.setsockopt(zmq.RCVTIMEO, 500)
+    proc = subprocess.Popen([sys.executable, os.path.join(ROOT, "tools", "replay_payloads.py"), str(cpu), "--bind", "tcp://127.0.0.1:%d" % port, "--settle", "1.5"],
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    got = {}
+    try:
+        sub.connect("tcp://127.0.0.1:%d" % port)
+        quiet = 0
+        while quiet < 3:
+            try:
+                topic, rate, payload = sub.recv_multipart()
+                got.setdefault(topic.rstrip(b"\0").decode(), []).append((struct.unpack("<I", rate)[0], payload))
+                quiet = 0
+            except zmq.Again:
+                quiet = quiet + 1 if proc.poll() is not None else 0
+    finally:
+        if proc.poll() is None:
+            proc.kill()
+        sub.close(0)
+    assert proc.returncode == 0 and sorted(got) == sorted(sc["channels"])
+    z = tmp_path / "zmq"
+    z.mkdir()
+    for topic, msgs in got.items():
+        (z / (topic + ".i16")).write_bytes(b"".join(p for _, p in msgs))
+        (z / (topic + ".meta")).write_text("%d %d\n" % (msgs[0][0], len(msgs[0][1])))
+        assert (z / (topic + ".i16")).read_bytes() == (cpu / (topic + ".i16")).read_bytes()
+    decoded = _decode(z, sc["bitrate"])
+    for topic, msgs in sent.items():
+        assert set(decoded[topic]) == expected_records(msgs), topic
