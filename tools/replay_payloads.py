@@ -2,7 +2,7 @@
 """Replay recorded per-topic payload dumps to ZeroMQ in aero-publish's wire format, so that an
 UNCHANGED `aero-decode -p tcp://host:port -t <topic> -b <rate>` can consume them on a machine that has it
 (SURVEY.md section 8d item E / 8f-4). Frames: [first 5 bytes of topic][uint32 LE rate][payload]
-(/root/reference/publish/zmqpublisher.cpp:61-73; the reference's tools/audio-publisher emits the same).
+(/root/reference/publish/zmqpublisher.cpp:61-73; the reference's own test harness tools/audio-publisher:126-128 sends the same three frames).
 
 Dump directory layout (written by `aero-publish-b200 --dump DIR` or tools/oracle_payloads.py):
     DIR/<topic>.i16      concatenated payloads of that topic
