@@ -155,8 +155,8 @@ def test_reference_publisher_on_the_product_vfo_class_has_no_cpu_path(tmp_path):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(GPUVFO), reason="oracle/_ref/ref_publish_gpuvfo not built (make -C oracle refpublish_gpuvfo)")
-@pytest.mark.skipif(not os.environ.get("AERODDC_RUN_UNVERIFIED"),
-                    reason="built after round 1's GPU minutes were spent: not yet run on hardware, enable with AERODDC_RUN_UNVERIFIED=1")
+@pytest.mark.xfail(not os.environ.get("AERODDC_RUN_UNVERIFIED"), strict=False,
+                   reason="built after round 1's GPU minutes were spent: its first hardware run is the round-end suite; XPASS = it works")
 @pytest.mark.parametrize("name,fmt,dcc", [("e2e_288k.ini", "cu8", True), ("two_mains_1920k.ini", "cf32", False)])
 def test_reference_publisher_source_drives_the_product_vfo_class(tmp_path, name, fmt, dcc):
     """Drop-in at link level: the reference's own Publisher (settings, reader loop, DC correction - all its code) calls
@@ -169,7 +169,7 @@ def test_reference_publisher_source_drives_the_product_vfo_class(tmp_path, name,
     assert rc == 0
     gpu = tmp_path / "gpu"
     gpu.mkdir()
-    r = subprocess.run([GPUVFO, ini, str(iq), fmt, "1" if dcc else "0", str(gpu)], capture_output=True, text=True)
+    r = subprocess.run([GPUVFO, ini, str(iq), fmt, "1" if dcc else "0", str(gpu)], capture_output=True, text=True, timeout=180)
     assert r.returncode == 0, r.stderr[-400:]
     names = sorted(os.listdir(tmp_path / "ref"))
     assert names == sorted(os.listdir(gpu)) and names
