@@ -92,7 +92,15 @@ struct HbState { P2 e[5]; P2 o[3]; };
 __device__ __forceinline__ P2 hb_out(const Ones& k, P2 e0, P2 e1, P2 e2, P2 e3, P2 e4, P2 xe, P2 o0) {
   P2 s0 = add2(k, e0, xe), s2 = add2(k, e1, e4), s4 = add2(k, e2, e3);
   P2 m0 = mul2s(s0, HB_P0), m2 = mul2s(s2, HB_P2), m4 = mul2s(s4, HB_P4), m5 = mul2s(o0, HB_P5);
+#ifdef AERODDC_HB_CENTER_FMA
+  // Experiment, off by default (make EXTRA=-DAERODDC_HB_CENTER_FMA): the centre tap is 0.5, so 0.5*w5 is exact and one
+  // fused multiply-add rounds exactly like the reference's separate product and sum unless w5 is denormal. Checked on
+  // the CPU oracle; needs a hardware parity run before it may become the default.
+  (void)m5;
+  return fma2(o0, bcast2(HB_P5), add2(k, add2(k, m0, m2), m4));
+#else
   return add2(k, add2(k, add2(k, m0, m2), m4), m5);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
