@@ -169,7 +169,7 @@ def test_reference_publisher_source_drives_the_product_vfo_class(tmp_path, name,
     assert rc == 0
     gpu = tmp_path / "gpu"
     gpu.mkdir()
-    r = subprocess.run([GPUVFO, ini, str(iq), fmt, "1" if dcc else "0", str(gpu)], capture_output=True, text=True, timeout=180)
+    r = subprocess.run([GPUVFO, ini, str(iq), fmt, "1" if dcc else "0", str(gpu)], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0, r.stderr[-400:]
     names = sorted(os.listdir(tmp_path / "ref"))
     assert names == sorted(os.listdir(gpu)) and names
