@@ -52,6 +52,7 @@ ABI_SYMBOLS = [
     "aeroddc_fleet_create", "aeroddc_fleet_add_vfo", "aeroddc_fleet_set_mode", "aeroddc_fleet_finalize", "aeroddc_fleet_host_slot",
     "aeroddc_fleet_submit", "aeroddc_fleet_wait", "aeroddc_fleet_process", "aeroddc_fleet_output", "aeroddc_fleet_num_devices",
     "aeroddc_fleet_device_of", "aeroddc_fleet_destroy", "aeroddc_bank_set_dc_correction", "aeroddc_fleet_set_dc_correction",
+    "aeroddc_bank_reset", "aeroddc_fleet_reset", "aeroddc_fleet_exchange", "aeroddc_dev_upload_async", "aeroddc_bank_submit_device_sliced",
     "aeroddc_dev_alloc", "aeroddc_dev_free", "aeroddc_dev_upload", "aeroddc_ipc_export", "aeroddc_ipc_import", "aeroddc_ipc_close", "aeroddc_enable_peer", "aeroddc_plan_segments",
 ]
 
@@ -73,6 +74,9 @@ def lib():
         L.aeroddc_bank_process.argtypes = [vp, vp, cz]
         L.aeroddc_bank_submit.argtypes = [vp, vp, cz]
         L.aeroddc_bank_wait.argtypes = [vp]
+        L.aeroddc_bank_reset.argtypes = [vp]
+        L.aeroddc_bank_submit_device_sliced.argtypes = [vp, ctypes.POINTER(vp), ci, cz, cz, ctypes.POINTER(vp), ci]
+        L.aeroddc_fleet_reset.argtypes = [vp]
         L.aeroddc_bank_host_slot.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(cz)]
         L.aeroddc_bank_submit_device.argtypes = [vp, vp, cz, vp]
         L.aeroddc_bank_output.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(cz), ctypes.POINTER(ctypes.c_uint32)]
@@ -90,6 +94,7 @@ def lib():
         L.aeroddc_dev_alloc.argtypes = [ci, cz, ctypes.POINTER(vp)]
         L.aeroddc_dev_free.argtypes = [ci, vp]
         L.aeroddc_dev_upload.argtypes = [ci, vp, vp, cz]
+        L.aeroddc_dev_upload_async.argtypes = [ci, vp, vp, cz, vp]
         L.aeroddc_ipc_export.argtypes = [ci, vp, ctypes.c_char_p]
         L.aeroddc_ipc_import.argtypes = [ci, ctypes.c_char_p, ctypes.POINTER(vp)]
         L.aeroddc_ipc_close.argtypes = [ci, vp]
@@ -105,6 +110,7 @@ def lib():
         L.aeroddc_fleet_process.argtypes = [vp, vp, cz]
         L.aeroddc_fleet_output.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(cz), ctypes.POINTER(ctypes.c_uint32)]
         L.aeroddc_fleet_num_devices.argtypes = [vp]
+        L.aeroddc_fleet_exchange.argtypes = [vp]
         L.aeroddc_fleet_device_of.argtypes = [vp, ci]
         L.aeroddc_fleet_destroy.argtypes = [vp]
         L.aeroddc_fleet_destroy.restype = None
@@ -159,6 +165,11 @@ def dev_free(device, ptr):
 def dev_upload(device, ptr, array):
     a = np.ascontiguousarray(array)
     _check(lib().aeroddc_dev_upload(device, ptr, a.ctypes.data, a.nbytes))
+
+
+def dev_upload_async(device, ptr, pinned_array, stream):
+    """cudaMemcpyAsync H2D of a contiguous view of pinned host memory on the given cudaStream_t."""
+    _check(lib().aeroddc_dev_upload_async(device, ptr, pinned_array.ctypes.data, pinned_array.nbytes, stream))
 
 
 def ipc_export(device, ptr):
@@ -243,8 +254,18 @@ class Bank:
     def submit_device(self, dev_ptr, ready_event=None):
         _check(self._L.aeroddc_bank_submit_device(self._h, int(dev_ptr), self.block_len, ready_event))
 
+    def submit_device_sliced(self, slice_ptrs, slice_len, ready_events=()):
+        """The block lies in len(slice_ptrs) device buffers of slice_len complex samples each (possibly on different GPUs)."""
+        sl = (ctypes.c_void_p * len(slice_ptrs))(*[int(p) for p in slice_ptrs])
+        ev = (ctypes.c_void_p * max(len(ready_events), 1))(*[int(e) if e else None for e in ready_events])
+        _check(self._L.aeroddc_bank_submit_device_sliced(self._h, sl, len(slice_ptrs), int(slice_len), self.block_len, ev, len(ready_events)))
+
     def wait(self):
         _check(self._L.aeroddc_bank_wait(self._h))
+
+    def reset(self):
+        """Rewind to stream position 0 (fresh filter/oscillator state); nothing may be in flight."""
+        _check(self._L.aeroddc_bank_reset(self._h))
 
     def host_slot(self, slot):
         """numpy view of pinned staging slot 0/1 (dtype of the input format, 2*block_len values)."""
@@ -342,6 +363,9 @@ class Fleet:
     def wait(self):
         _check(self._L.aeroddc_fleet_wait(self._h))
 
+    def reset(self):
+        _check(self._L.aeroddc_fleet_reset(self._h))
+
     def host_slot(self, slot):
         p, n = ctypes.c_void_p(), ctypes.c_size_t()
         _check(self._L.aeroddc_fleet_host_slot(self._h, slot, ctypes.byref(p), ctypes.byref(n)))
@@ -358,6 +382,10 @@ class Fleet:
 
     def device_of(self, vfo):
         return self._L.aeroddc_fleet_device_of(self._h, vfo)
+
+    @property
+    def exchange(self):
+        return {0: "single", 1: "peer", 2: "nccl"}[self._L.aeroddc_fleet_exchange(self._h)]
 
     def close(self):
         if self._h:

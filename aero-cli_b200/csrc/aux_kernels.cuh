@@ -192,19 +192,26 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(const TailVfo* __res
 // DC removal of Publisher::demodData (publisher.cpp:292-296), exact and therefore sequential:
 //   avept = avept * (1.0f - 0.000001f) + 0.000001f * x;  x -= avept      (std::complex<float> ops = per rail)
 // thread 0 walks the I rail, thread 1 the Q rail; the running average persists in `state` across blocks.
+// The block may come in slices (RawBlock, ddc_kernels.cuh); the walk goes slice by slice.
 template <int FMT>
-__global__ void dcc_kernel(const void* __restrict__ raw, float* __restrict__ out, float* __restrict__ state, int n) {
+__global__ void dcc_kernel(const RawBlock rb, float* __restrict__ out, float* __restrict__ state, int n) {
   const int rail = threadIdx.x;
   if (rail > 1) return;
   const float k = 1.0f - 0.000001f, c = 0.000001f;
   float a = state[rail];
-  for (int i = 0; i < n; ++i) {
-    float x;
-    if (FMT == 0) x = __fdiv_rn(__fsub_rn((float)reinterpret_cast<const unsigned char*>(raw)[2 * i + rail], 127.4f), 128.0f);
-    else if (FMT == 1) x = __fdiv_rn((float)reinterpret_cast<const short*>(raw)[2 * i + rail], 32768.0f);
-    else x = reinterpret_cast<const float*>(raw)[2 * i + rail];
-    a = __fadd_rn(__fmul_rn(a, k), __fmul_rn(c, x));
-    out[2 * i + rail] = __fsub_rn(x, a);
+  for (int s = 0, done = 0; s < rb.n_slices && done < n; ++s) {
+    const void* raw = rb.slice[s];
+    const int m = min(rb.slice_len, n - done);
+    float* o = out + 2 * (size_t)done;
+    for (int i = 0; i < m; ++i) {
+      float x;
+      if (FMT == 0) x = __fdiv_rn(__fsub_rn((float)reinterpret_cast<const unsigned char*>(raw)[2 * i + rail], 127.4f), 128.0f);
+      else if (FMT == 1) x = __fdiv_rn((float)reinterpret_cast<const short*>(raw)[2 * i + rail], 32768.0f);
+      else x = reinterpret_cast<const float*>(raw)[2 * i + rail];
+      a = __fadd_rn(__fmul_rn(a, k), __fmul_rn(c, x));
+      o[2 * i + rail] = __fsub_rn(x, a);
+    }
+    done += m;
   }
   state[rail] = a;
 }

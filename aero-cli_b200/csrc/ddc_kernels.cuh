@@ -5,17 +5,22 @@
 //   Oscillator (NCO recurrence)  /root/reference/publish/oscillator.cpp:4-39
 //   HalfBandDecimator::decimate  /root/reference/publish/halfbanddecimator.cpp:35-60
 //   FIR half-band queue kernels  /root/reference/publish/dsp.cpp:102-172
-//   usb_demod / usb_decimdemod   /root/reference/publish/vfo.cpp:188-258
-//   compress                     /root/reference/publish/vfo.cpp:260-287
 //
 // Design: one thread carries ONE VFO through time; its I and Q rails sit in the two
 // lanes of the Blackwell packed-FP32 instructions (FMUL2/FFMA2, PTX mul/fma.rn.f32x2). Every multiply
 // and add of the reference is issued un-fused and in the reference's order, so results are
 // bit-identical to the CPU chain; packing halves the issue slots per flop, which leaves room for the
 // shared-memory broadcast loads and register moves next to a saturated FP32 pipe.
-// The raw IQ tile is staged once per CTA in shared memory (TMA bulk copy) and broadcast to the 128
-// VFOs of the CTA. Time is cut into segments (each warmed up over the 10*2^D samples before it) and
-// every segment into chained parts whose state is handed from CTA to CTA through HBM.
+//
+// Two kernels share the half-band cascade:
+//   ddc_main_kernel  unpack + NCO + mix + the first min(D, 5) half-band stages, all in registers. A CTA is ONE warp
+//                    (32 VFOs) with its own TMA ring of raw tiles; time is cut into segments (each warmed up over the
+//                    10*(2^5-1) samples before it) and every segment into chained parts whose state is handed from
+//                    CTA to CTA through HBM. Output: the stage-min(D,5) stream, [time][VFO] (coalesced).
+//   ddc_deep_kernel  the remaining D-5 stages (rate <= Fs/32) from that stream: one warp = 32 VFOs x one time
+//                    range, history in registers, warmed up over 10*(2^(D-5)-1) of its own input samples.
+// The raw block may be given as up to 8 equal slices living in different GPUs' HBM (peer memory over NVLink): the TMA
+// tile loads pull each tile from the slice that holds it, so the exchange is fused with the compute tile by tile.
 // Only bank.cu includes this header (compute-only translation unit; no host-side state here).
 #pragma once
 #include <cstdint>
@@ -23,16 +28,18 @@
 
 namespace aeroddc {
 
-constexpr int kThreads = 128;          // threads per CTA; each thread carries one VFO
+constexpr int kThreads = 32;           // threads per CTA of the main kernel: one warp, each thread carries one VFO
 constexpr int kVfoPerCta = kThreads;
 constexpr int kChunk = 32;             // input samples per unrolled inner step
 constexpr int kTile = 256;             // input samples per shared-memory tile
 constexpr int kMaxStages = 8;          // hdecimator[8], vfo.h:63
-constexpr int kFastStages = 5;         // half-band stages kept in registers
+constexpr int kFastStages = 5;         // half-band stages of the main kernel (registers); the rest run in the deep kernel
+constexpr int kDeepStages = kMaxStages - kFastStages;
 constexpr int kStateSlots = 8;         // per stage: 5 even-phase + 3 odd-phase history samples
 constexpr int kNcoStride = 256;        // NCO checkpoint spacing (samples)
-constexpr int kHandSlots = kMaxStages * kStateSlots + 1;   // half-band history of every stage + oscillator state
-constexpr int kCtasPerSm = 4;          // 16 resident warps per SM at <= 128 registers per thread
+constexpr int kHandSlots = kFastStages * kStateSlots + 1;   // half-band history of the register stages + oscillator state
+constexpr int kCtasPerSm = 16;         // 16 resident warps per SM at <= 128 registers per thread
+constexpr int kMaxSlices = 8;          // a raw block may be spread over up to 8 GPUs
 
 enum { FMT_CU8 = 0, FMT_CS16 = 1, FMT_CF32 = 2 };
 
@@ -88,18 +95,19 @@ __device__ __forceinline__ P2 mix(const Ones& k, float a, float b, const float2&
 struct HbState { P2 e[5]; P2 o[3]; };
 
 // y[j] = ((p0*(w0+w10) + p2*(w2+w8)) + p4*(w4+w6)) + p5*w5, w[t] = x[2j-10+t]  (dsp.cpp:141-147),
-// both rails at once
+// both rails at once.
+// The centre tap is exactly 0.5: fl(0.5*w5) is exact for every normal w5 (a halving changes only the exponent), so
+// fl(acc + fl(0.5*w5)) == fma(0.5, w5, acc) bit for bit. The two forms can differ only when w5 is so small that its
+// half is not representable (|w5| < 2^-125) AND acc is subnormal too, i.e. on signals below 1e-37 of full scale; such
+// values end as 0 in every int16 / int8 payload either way (tests/test_gpu_parity.py::test_subnormal_inputs_...).
+// -DAERODDC_HB_CENTER_MUL restores the separate multiply (one more FMUL2 per half-band output).
 __device__ __forceinline__ P2 hb_out(const Ones& k, P2 e0, P2 e1, P2 e2, P2 e3, P2 e4, P2 xe, P2 o0) {
   P2 s0 = add2(k, e0, xe), s2 = add2(k, e1, e4), s4 = add2(k, e2, e3);
-  P2 m0 = mul2s(s0, HB_P0), m2 = mul2s(s2, HB_P2), m4 = mul2s(s4, HB_P4), m5 = mul2s(o0, HB_P5);
-#ifdef AERODDC_HB_CENTER_FMA
-  // Experiment, off by default (make EXTRA=-DAERODDC_HB_CENTER_FMA): the centre tap is 0.5, so 0.5*w5 is exact and one
-  // fused multiply-add rounds exactly like the reference's separate product and sum unless w5 is denormal. Checked on
-  // the CPU oracle; needs a hardware parity run before it may become the default.
-  (void)m5;
+  P2 m0 = mul2s(s0, HB_P0), m2 = mul2s(s2, HB_P2), m4 = mul2s(s4, HB_P4);
+#ifndef AERODDC_HB_CENTER_MUL
   return fma2(o0, bcast2(HB_P5), add2(k, add2(k, m0, m2), m4));
 #else
-  return add2(k, add2(k, add2(k, m0, m2), m4), m5);
+  return add2(k, add2(k, add2(k, m0, m2), m4), mul2s(o0, HB_P5));
 #endif
 }
 
@@ -131,33 +139,48 @@ __device__ __forceinline__ P2 hb_out_fast(const Ones& k, P2 e0, P2 e1, P2 e2, P2
   return fma2(s4, bcast2(HB_P4), fma2(o0, bcast2(HB_P5), fma2(s2, bcast2(HB_P2), mul2s(s0, HB_P0))));
 }
 
-// consume the pair (x[2j], x[2j+1]) and return output j
+// feed the even-phase sample x[2j] and return output j; then feed the odd-phase sample x[2j+1]
 template <bool FAST>
-__device__ __forceinline__ P2 hb_pair(const Ones& k, HbState& h, P2 xe, P2 xo) {
+__device__ __forceinline__ P2 hb_even(const Ones& k, HbState& h, P2 xe) {
   const P2 y = FAST ? hb_out_fast(k, h.e[0], h.e[1], h.e[2], h.e[3], h.e[4], xe, h.o[0])
                     : hb_out(k, h.e[0], h.e[1], h.e[2], h.e[3], h.e[4], xe, h.o[0]);
   h.e[0] = h.e[1]; h.e[1] = h.e[2]; h.e[2] = h.e[3]; h.e[3] = h.e[4]; h.e[4] = xe;
-  h.o[0] = h.o[1]; h.o[1] = h.o[2]; h.o[2] = xo;
+  return y;
+}
+__device__ __forceinline__ void hb_odd(HbState& h, P2 xo) { h.o[0] = h.o[1]; h.o[1] = h.o[2]; h.o[2] = xo; }
+// consume the pair (x[2j], x[2j+1]) and return output j
+template <bool FAST>
+__device__ __forceinline__ P2 hb_pair(const Ones& k, HbState& h, P2 xe, P2 xo) {
+  const P2 y = hb_even<FAST>(k, h, xe);
+  hb_odd(h, xo);
   return y;
 }
 
 // ---------------------------------------------------------------------------------------------
 // kernel parameters
 // ---------------------------------------------------------------------------------------------
+struct RawBlock {
+  const void* slice[kMaxSlices];   // slice i holds samples [i*slice_len, (i+1)*slice_len) of the block, format FMT
+  int n_slices;
+  int slice_len;                   // complex samples per slice (even; the last slice may be shorter)
+};
+
 struct MainParams {
-  const void* iq;            // raw block on the device, B complex samples of format FMT
+  RawBlock raw;              // the block on the device(s), B complex samples
   const float2* ckpt;        // [nck][vfo_pitch] NCO state after k*kNcoStride steps from (1,0)
   const float2* rot;         // [vfo_pitch] per-VFO rotation (cos, sin) as floats
   const float2* qlast;       // [vfo_pitch] q[L-1], the value sample 0 is mixed with
   const float2* state_in;    // [kMaxStages][kStateSlots][vfo_pitch] history at the start of this block
   float2* state_out;         // same layout, history for the start of the next block
-  float2* const* xd_rows;    // [vfo_pitch] per VFO: where stage-D sample 0 of this block goes (history lies in front)
+  const unsigned char* vfo_D; // [vfo_pitch] half-band stages of each VFO (the boundary role rebuilds all of them)
+  float2* mid;               // [B >> DA][mid_pitch] output: the stage-DA stream of this block, VFO (of this launch) fastest
+  int mid_pitch;
   long long block_abs;       // absolute index of the block's first sample
-  int vfo_pitch;             // padded VFO count (row pitch of ckpt/rot/state)
-  int vfo_base, vfo_count;   // VFO slice handled by this launch (all share D)
-  int D;                     // half-band stages
+  int vfo_pitch;             // padded VFO count (row pitch of ckpt/rot/state/mid)
+  int vfo_base, vfo_count;   // VFO slice handled by this launch (all share DA = min(D, 5))
+  int DA;                    // half-band stages of this kernel
   int B, S, W, nseg;         // block length, segment length, warm-up length, segments per block
-  int Wb;                    // warm-up of the boundary role: 11*2^D (it needs 11 samples of history per stage)
+  int Wb;                    // warm-up of the boundary role: 11*2^Dmax (it needs 11 samples of history per stage)
   int nco_len;               // L = (int)Fs, the oscillator table length
   float one;                 // 1.0f (see add2)
   int transient;             // tolerance mode: table indices below this use the full recurrence
@@ -203,27 +226,38 @@ template <int FMT> __device__ __forceinline__ float2 load_raw(const void* base, 
   if (FMT == FMT_CS16) { const short2 v = reinterpret_cast<const short2*>(base)[n]; return make_float2(cvt_s16(v.x), cvt_s16(v.y)); }
   return reinterpret_cast<const float2*>(base)[n];
 }
+// sample n of a (possibly sliced) block
+template <int FMT> __device__ __forceinline__ float2 load_raw_block(const RawBlock& rb, int n) {
+  const int s = rb.n_slices > 1 ? n / rb.slice_len : 0;
+  return load_raw<FMT>(rb.slice[s], (size_t)(n - s * rb.slice_len));
+}
 
 // ---------------------------------------------------------------------------------------------
-// The register-resident part of the cascade: kChunk input samples -> kChunk >> NF outputs.
-// SPECIAL handles the two rare events inside a chunk: oscillator table wrap (index reaches L:
-// restart from (1,0), oscillator.cpp:31-39) and absolute sample 0 (mixed with q[L-1], because the
-// constructor leaves _vector at the last table entry, oscillator.cpp:12-27).
+// The register-resident cascade: kChunk input samples -> kChunk >> NF outputs.
+// SPECIAL handles the rare events inside a chunk: oscillator table wrap (index reaches L: restart from (1,0),
+// oscillator.cpp:31-39), absolute sample 0 (mixed with q[L-1], because the constructor leaves _vector at the last
+// table entry, oscillator.cpp:12-27) and, in tolerance mode, a checkpoint stride boundary that does not fall on a
+// chunk start (possible after a table wrap when L is not a multiple of the chunk).
 // ---------------------------------------------------------------------------------------------
 template <int NF, bool SPECIAL, bool FAST>
 __device__ __forceinline__ void fast_chunk(const Ones& k1, float& oa, float& ob, const Rot& rot,
                                            HbState (&hb)[kFastStages > 0 ? kFastStages : 1],
                                            const float2* __restrict__ tile, P2 (&out)[kChunk >> NF],
-                                           int& idx, int nco_len, long long n_abs, float qa, float qb) {
+                                           int& idx, int nco_len, long long n_abs, float qa, float qb,
+                                           const float2* __restrict__ ckpt_col, int vfo_pitch, int transient) {
   P2 x0[kChunk];
 #pragma unroll
   for (int i = 0; i < kChunk; ++i) {
     const float2 s = tile[i];   // one raw sample (c, d), broadcast to the warp
     if (SPECIAL) {
       if (idx == nco_len) { idx = 0; oa = 1.0f; ob = 0.0f; }
+      if (FAST && idx >= transient && (idx % kNcoStride) == 0) {   // snap back to the exact table
+        const float2 c0 = ckpt_col[(size_t)(idx / kNcoStride) * vfo_pitch];
+        oa = c0.x; ob = c0.y;
+      }
     }
     if (!FAST) nco_step(k1, oa, ob, rot);
-    else if (SPECIAL) nco_step_fused(oa, ob, rot);     // restart transient: full recurrence
+    else if (SPECIAL) { if (idx < transient) nco_step_fused(oa, ob, rot); else nco_rotate_fast(oa, ob, rot); }
     else nco_rotate_fast(oa, ob, rot);
     float a = oa, b = ob;
     if (SPECIAL) { if (n_abs + i == 0) { a = qa; b = qb; } idx++; }
@@ -240,30 +274,6 @@ __device__ __forceinline__ void fast_chunk(const Ones& k1, float& oa, float& ob,
   for (int i = 0; i < (kChunk >> NF); ++i) out[i] = x0[i];
 }
 
-// ---------------------------------------------------------------------------------------------
-// Deep stages (>= kFastStages): history lives in shared memory, [stage][slot][thread], one (I,Q)
-// pair per entry: slots 0..4 = even-phase history (oldest first), 5..7 = odd-phase history.
-// ---------------------------------------------------------------------------------------------
-struct DeepSmem {
-  P2* base;   // this thread's column: element (stage, slot) at base[(stage*kStateSlots + slot) * kThreads]
-  __device__ __forceinline__ P2& at(int stage, int slot) const { return base[(stage * kStateSlots + slot) * kThreads]; }
-};
-
-// push one sample into deep stage `ds`; returns true and the output in y when the sample was even-phase
-template <bool FAST>
-__device__ __forceinline__ bool deep_push(const Ones& k1, const DeepSmem& sm, int ds, bool odd, P2 x, P2& y) {
-  if (odd) {   // store x[2j+1]
-    sm.at(ds, 5) = sm.at(ds, 6);
-    sm.at(ds, 6) = sm.at(ds, 7);
-    sm.at(ds, 7) = x;
-    return false;
-  }
-  const P2 e0 = sm.at(ds, 0), e1 = sm.at(ds, 1), e2 = sm.at(ds, 2), e3 = sm.at(ds, 3), e4 = sm.at(ds, 4), o0 = sm.at(ds, 5);
-  y = FAST ? hb_out_fast(k1, e0, e1, e2, e3, e4, x, o0) : hb_out(k1, e0, e1, e2, e3, e4, x, o0);
-  sm.at(ds, 0) = e1; sm.at(ds, 1) = e2; sm.at(ds, 2) = e3; sm.at(ds, 3) = e4; sm.at(ds, 4) = x;
-  return true;
-}
-
 __device__ __forceinline__ P2 load_p2(const float2* p) { const float2 v = *p; return pack2(v.x, v.y); }
 __device__ __forceinline__ void store_p2(float2* p, P2 c) { float a, b; unpack2(c, a, b); *p = make_float2(a, b); }
 
@@ -275,8 +285,10 @@ __device__ __forceinline__ void store_p2(float2* p, P2 c) { float a, b; unpack2(
 // is dropped and the window is one sample older than the true one. In polyphase terms the next
 // block's even-phase history is this block's odd samples o[n/2-6 .. n/2-2] and its odd-phase
 // history is this block's even samples e[n/2-3 .. n/2-1].
-// Straightforward per-thread code with local-memory rings; it runs on one extra CTA per VFO group
-// concurrently with the segment CTAs, so its speed does not matter.
+// Straightforward per-thread code with local-memory rings; it runs on one extra CTA per 32 VFOs
+// concurrently with the segment CTAs (it takes the first tickets), so its speed does not matter.
+// VFOs of one launch may differ in D (they share min(D, 5)): every thread walks the same Wb = 11*2^Dmax samples -
+// a longer run-in than its own 11*2^D leaves the same final history - with its own stage count.
 // ---------------------------------------------------------------------------------------------
 template <int FMT, bool FAST>
 __device__ void boundary_role(const MainParams& p, int vfo, bool active) {
@@ -291,6 +303,7 @@ __device__ void boundary_role(const MainParams& p, int vfo, bool active) {
   const float2 r = p.rot[vfo];
   Rot rot; rot.a = pack2(r.x, r.y); rot.b = pack2(-r.y, r.x);
   const float2 ql = p.qlast[vfo];
+  const int D = p.vfo_D[vfo];
   const int start = p.B - p.Wb;                      // in-block index of the first warm-up sample
   const long long n0 = p.block_abs + start;
   int idx = (int)(n0 % p.nco_len);
@@ -302,7 +315,7 @@ __device__ void boundary_role(const MainParams& p, int vfo, bool active) {
     for (int i = 0; i < rem; ++i) nco_step(k1, oa, ob, rot);
   }
   for (int i = 0; i < p.Wb; ++i) {
-    const float2 cd = load_raw<FMT>(p.iq, (size_t)start + i);
+    const float2 cd = load_raw_block<FMT>(p.raw, start + i);
     if (idx == p.nco_len) { idx = 0; oa = 1.0f; ob = 0.0f; }
     if (FAST && (idx % kNcoStride) == 0) { const float2 c = p.ckpt[(size_t)(idx / kNcoStride) * p.vfo_pitch + vfo]; oa = c.x; ob = c.y; }
     if (!FAST) nco_step(k1, oa, ob, rot);
@@ -314,7 +327,7 @@ __device__ void boundary_role(const MainParams& p, int vfo, bool active) {
     P2 x = FAST ? mix_fast(a, b, cd) : mix(k1, a, b, cd);
     int cnt = i;
 #pragma unroll 1
-    for (int s = 0; s < p.D; ++s) {
+    for (int s = 0; s < D; ++s) {
       if (cnt & 1) {
         for (int k = 0; k < 5; ++k) oh[s][k] = oh[s][k + 1];
         oh[s][5] = x;
@@ -330,7 +343,7 @@ __device__ void boundary_role(const MainParams& p, int vfo, bool active) {
   }
   if (active) {
 #pragma unroll 1
-    for (int s = 0; s < p.D; ++s) {
+    for (int s = 0; s < D; ++s) {
       float2* st = p.state_out + (size_t)s * kStateSlots * p.vfo_pitch + vfo;
       for (int k = 0; k < 5; ++k) store_p2(st + (size_t)k * p.vfo_pitch, oh[s][k]);            // o[n/2-6 .. n/2-2]
       for (int k = 0; k < 3; ++k) store_p2(st + (size_t)(5 + k) * p.vfo_pitch, eh[s][2 + k]);  // e[n/2-3 .. n/2-1]
@@ -339,16 +352,15 @@ __device__ void boundary_role(const MainParams& p, int vfo, bool active) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Main kernel. 1-D grid: ngroups boundary CTAs, then Q * nseg * ngroups segment-part CTAs.
-// Shared memory: raw tile ring (TMA bulk copies) | converted float tiles (c, d), double-buffered |
-// deep-stage history | mbarriers.
+// Main kernel. 1-D grid of one-warp CTAs: ngroups boundary CTAs, then Q * nseg * ngroups segment-part CTAs.
+// Shared memory: raw tile ring (TMA bulk copies) | one converted float tile (cu8 / cs16 only; cf32 tiles are read
+// where the TMA put them) | mbarriers.
 // ---------------------------------------------------------------------------------------------
 template <int FMT> struct TileSmem {
   static constexpr int kRawStages = 3;
   static constexpr int kRawBytes = kTile * RawBytes<FMT>::v;
-  static constexpr int kCvtBytes = 2 * kTile * 8;
-  static constexpr int kDeepBytes = (kMaxStages - kFastStages) * kStateSlots * kThreads * 8;
-  static constexpr int kTotal = kRawStages * kRawBytes + kCvtBytes + kDeepBytes + 64;
+  static constexpr int kCvtBytes = FMT == FMT_CF32 ? 0 : kTile * 8;
+  static constexpr int kTotal = kRawStages * kRawBytes + kCvtBytes + 64;
 };
 
 template <int NF, int FMT, bool FAST>
@@ -357,17 +369,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
   using TS = TileSmem<FMT>;
   unsigned char* raw = smem;
   float2* cvt = reinterpret_cast<float2*>(smem + TS::kRawStages * TS::kRawBytes);
-  P2* deep = reinterpret_cast<P2*>(smem + TS::kRawStages * TS::kRawBytes + TS::kCvtBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TS::kRawStages * TS::kRawBytes + TS::kCvtBytes + TS::kDeepBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TS::kRawStages * TS::kRawBytes + TS::kCvtBytes);
 
   const int tid = threadIdx.x;
   // 1-D grid. Work items are numbered [boundary CTA of every VFO group], then part 0 of every (group, segment), then
   // part 1 of every (group, segment), ... and a CTA takes the next number when it STARTS (atomic ticket), so the
   // predecessor in its chain has always started before it - whatever order the hardware dispatches blocks in.
-  __shared__ int s_ticket;
-  if (tid == 0) s_ticket = atomicAdd(p.ticket, 1);
-  __syncthreads();
-  int bid = s_ticket;
+  int bid = 0;
+  if (tid == 0) bid = atomicAdd(p.ticket, 1);
+  bid = __shfl_sync(0xffffffffu, bid, 0);
   const bool is_boundary = bid < p.ngroups;
   int q = 0, gy = bid, seg = 0;
   if (!is_boundary) {
@@ -380,10 +390,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
   }
   const int slot = gy * kVfoPerCta + tid;               // this thread's VFO within the slice
   const bool active = slot < p.vfo_count;
-  const int vfo = p.vfo_base + (active ? slot : 0);     // inactive threads shadow VFO 0 of the slice, never store
+  const int vfo = p.vfo_base + (active ? slot : 0);     // inactive lanes shadow VFO 0 of the slice, never store
 
   if (is_boundary) {
-    if (p.D > 0) boundary_role<FMT, FAST>(p, vfo, active);
+    boundary_role<FMT, FAST>(p, vfo, active);
     return;
   }
 
@@ -394,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
   const bool empty = part_start >= seg_end;               // short last segment: nothing left for this part
   const int warm = (q > 0 || seg == 0) ? 0 : p.W;         // part 0 of segment 0 starts from the saved block history
   const int first = part_start - warm;                    // in-block index of the first sample processed
-  const int total = empty ? 0 : warm + (part_end - part_start);   // multiple of max(kChunk, 2^D)
+  const int total = empty ? 0 : warm + (part_end - part_start);   // multiple of max(kChunk, 2^DA)
   const int ntiles = (total + kTile - 1) / kTile;
   int* flag = p.flags + gy * p.nseg + seg;
   float2* hand = p.hand + ((size_t)(gy * p.nseg + seg) * kHandSlots) * kThreads + tid;
@@ -403,14 +413,20 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
     for (int i = 0; i < TS::kRawStages; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
-  const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(p.iq) + (size_t)first * RawBytes<FMT>::v;
+  __syncwarp();
+  // tile t = samples [first + t*kTile, ...) of the block; a tile that straddles two slices takes two bulk copies
   auto issue = [&](int t) {
     const int n = min(kTile, total - t * kTile);
-    const unsigned bytes = (unsigned)n * RawBytes<FMT>::v;
+    const int g = first + t * kTile;
     uint64_t* bar = &bars[t % TS::kRawStages];
-    mbar_expect_tx(bar, bytes);
-    tma_bulk_g2s(raw + (t % TS::kRawStages) * TS::kRawBytes, gsrc + (size_t)t * TS::kRawBytes, bytes, bar);
+    unsigned char* dst = raw + (t % TS::kRawStages) * TS::kRawBytes;
+    mbar_expect_tx(bar, (unsigned)n * RawBytes<FMT>::v);
+    const int s = p.raw.n_slices > 1 ? g / p.raw.slice_len : 0;
+    const int off = g - s * p.raw.slice_len;
+    const int n1 = p.raw.n_slices > 1 ? min(n, p.raw.slice_len - off) : n;
+    tma_bulk_g2s(dst, reinterpret_cast<const unsigned char*>(p.raw.slice[s]) + (size_t)off * RawBytes<FMT>::v, (unsigned)n1 * RawBytes<FMT>::v, bar);
+    if (n1 < n)
+      tma_bulk_g2s(dst + (size_t)n1 * RawBytes<FMT>::v, reinterpret_cast<const unsigned char*>(p.raw.slice[s + 1]), (unsigned)(n - n1) * RawBytes<FMT>::v, bar);
   };
   if (tid == 0) {
     for (int t = 0; t < TS::kRawStages && t < ntiles; ++t) issue(t);
@@ -421,9 +437,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
   const float2 r = p.rot[vfo];
   Rot rot; rot.a = pack2(r.x, r.y); rot.b = pack2(-r.y, r.x);
   const float2 ql = p.qlast[vfo];
+  const float2* ckpt_col = p.ckpt + vfo;
   HbState hb[kFastStages > 0 ? kFastStages : 1];
-  DeepSmem dsm; dsm.base = deep + tid;
-  const int ndeep = p.D > NF ? p.D - NF : 0;
   if (q > 0) {
     // wait for the previous part of this segment, then take over its state
     if (tid == 0) {
@@ -434,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
         if (seen != want) { __nanosleep(200); if (++spins > (1 << 24)) { *p.err = 1; break; } }
       } while (seen != want);
     }
-    __syncthreads();
+    __syncwarp();
     __threadfence();
 #pragma unroll
     for (int s = 0; s < NF; ++s) {
@@ -443,8 +458,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
 #pragma unroll
       for (int k = 0; k < 3; ++k) hb[s].o[k] = load_p2(hand + (size_t)(s * kStateSlots + 5 + k) * kThreads);
     }
-    for (int s = 0; s < ndeep; ++s)
-      for (int k = 0; k < kStateSlots; ++k) dsm.at(s, k) = load_p2(hand + (size_t)((NF + s) * kStateSlots + k) * kThreads);
   } else if (seg == 0) {
 #pragma unroll
     for (int s = 0; s < NF; ++s) {
@@ -454,10 +467,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
 #pragma unroll
       for (int k = 0; k < 3; ++k) hb[s].o[k] = load_p2(st + (size_t)(5 + k) * p.vfo_pitch);
     }
-    for (int s = 0; s < ndeep; ++s) {
-      const float2* st = p.state_in + (size_t)(NF + s) * kStateSlots * p.vfo_pitch + vfo;
-      for (int k = 0; k < kStateSlots; ++k) dsm.at(s, k) = load_p2(st + (size_t)k * p.vfo_pitch);
-    }
   } else {
 #pragma unroll
     for (int s = 0; s < NF; ++s) {
@@ -466,15 +475,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
 #pragma unroll
       for (int k = 0; k < 3; ++k) hb[s].o[k] = pzero();
     }
-    for (int s = 0; s < ndeep; ++s)
-      for (int k = 0; k < kStateSlots; ++k) dsm.at(s, k) = pzero();
   }
   long long n_abs = p.block_abs + first;
   int idx = (int)(n_abs % p.nco_len);
   float oa, ob;
   {
     const int ck = idx / kNcoStride, rem = idx % kNcoStride;
-    const float2 c = p.ckpt[(size_t)ck * p.vfo_pitch + vfo];
+    const float2 c = ckpt_col[(size_t)ck * p.vfo_pitch];
     oa = c.x; ob = c.y;
     for (int i = 0; i < rem; ++i) nco_step(k1, oa, ob, rot);
   }
@@ -483,68 +490,56 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
     oa = o.x; ob = o.y;
   }
 
-  // stage-D output cursor: outputs before the segment start (warm-up) are discarded
-  float2* xd = p.xd_rows[vfo];
-  const int out_first = part_start >> p.D;                // first stage-D index this part owns
-  int out_pos = first >> p.D;                             // stage-D index of the next output produced
-  unsigned chunk_ctr = 0;                                 // chunks since `first` (first is 2^D aligned)
+  // output cursor in the stage-DA stream: outputs before the part's own start (warm-up) are discarded
+  float2* mid = p.mid + (active ? slot : 0);
+  const int out_first = part_start >> NF;                 // first stage-DA index this part owns
+  int out_pos = first >> NF;                              // stage-DA index of the next output produced
   float2 nxt = make_float2(0.f, 0.f);                     // tolerance mode: prefetched checkpoint of stride nxt_k
   int nxt_k = -1;
 
   for (int t = 0; t < ntiles; ++t) {
     const int n = min(kTile, total - t * kTile);
     mbar_wait(&bars[t % TS::kRawStages], (t / TS::kRawStages) & 1);
-    // unpack once per CTA: raw -> float (c, d), shared by every VFO of the CTA
-    float2* dst = cvt + (t & 1) * kTile;
-    {
+    const float2* tile;
+    if (FMT == FMT_CF32) {
+      tile = reinterpret_cast<const float2*>(raw + (t % TS::kRawStages) * TS::kRawBytes);
+    } else {
+      // unpack once per CTA: raw -> float (c, d), shared by the 32 VFOs of the warp
       const unsigned char* src = raw + (t % TS::kRawStages) * TS::kRawBytes;
-      for (int i = tid; i < n; i += kThreads) dst[i] = load_raw<FMT>(src, i);
+      __syncwarp();   // every lane has finished reading the previous converted tile
+      for (int i = tid; i < n; i += kThreads) cvt[i] = load_raw<FMT>(src, i);
+      __syncwarp();
+      if (tid == 0 && t + TS::kRawStages < ntiles) issue(t + TS::kRawStages);   // the raw slot is free again
+      tile = cvt;
     }
-    __syncthreads();   // converted tile visible; everyone has finished computing on cvt[(t-1)&1]
-    if (tid == 0 && t + TS::kRawStages < ntiles) issue(t + TS::kRawStages);   // raw slot is free again
-    const float2* tile = dst;
 
 #pragma unroll 2
     for (int c = 0; c < n; c += kChunk) {
       P2 out[kChunk >> NF];
-      // rare variant: oscillator table wrap inside the chunk, absolute sample 0, and (tolerance mode) the restart transient
-      const bool special = (idx + kChunk > p.nco_len) || (n_abs == 0) || (FAST && idx < p.transient);
-      if (FAST && !special && (idx % kNcoStride) == 0) {   // tolerance mode: snap back to the exact table every stride
+      // rare variant: oscillator table wrap inside the chunk, absolute sample 0, and (tolerance mode) the restart
+      // transient or a checkpoint stride boundary strictly inside the chunk
+      const int in_stride = idx % kNcoStride;
+      const bool special = (idx + kChunk > p.nco_len) || (n_abs == 0) ||
+                           (FAST && (idx < p.transient || (in_stride != 0 && in_stride + kChunk > kNcoStride)));
+      if (FAST && !special && in_stride == 0) {   // tolerance mode: snap back to the exact table every stride
         const int kk = idx / kNcoStride;
-        const float2 c0 = (kk == nxt_k) ? nxt : p.ckpt[(size_t)kk * p.vfo_pitch + vfo];
+        const float2 c0 = (kk == nxt_k) ? nxt : ckpt_col[(size_t)kk * p.vfo_pitch];
         oa = c0.x; ob = c0.y;
         nxt_k = min(kk + 1, p.nck - 1);                     // prefetch the next stride's checkpoint (used 8 chunks later)
-        nxt = p.ckpt[(size_t)nxt_k * p.vfo_pitch + vfo];
+        nxt = ckpt_col[(size_t)nxt_k * p.vfo_pitch];
       }
-      if (special) fast_chunk<NF, true, FAST>(k1, oa, ob, rot, hb, tile + c, out, idx, p.nco_len, n_abs, ql.x, ql.y);
-      else         fast_chunk<NF, false, FAST>(k1, oa, ob, rot, hb, tile + c, out, idx, p.nco_len, n_abs, ql.x, ql.y);
+      if (special) fast_chunk<NF, true, FAST>(k1, oa, ob, rot, hb, tile + c, out, idx, p.nco_len, n_abs, ql.x, ql.y, ckpt_col, p.vfo_pitch, p.transient);
+      else         fast_chunk<NF, false, FAST>(k1, oa, ob, rot, hb, tile + c, out, idx, p.nco_len, n_abs, ql.x, ql.y, ckpt_col, p.vfo_pitch, p.transient);
       n_abs += kChunk;
-      if (NF < kFastStages) {
-        // D == NF < kFastStages: every fast output is a stage-D sample
 #pragma unroll
-        for (int i = 0; i < (kChunk >> NF); ++i) {
-          if (out_pos >= out_first && active) store_p2(xd + out_pos, out[i]);
-          out_pos++;
-        }
-      } else {
-        // one stage-kFastStages sample per chunk ripples through the deep stages
-        P2 x = out[0];
-        unsigned cc = chunk_ctr;
-        int s = 0;
-        bool produced = true;
-#pragma unroll 1
-        for (; s < ndeep; ++s) {
-          P2 y;
-          if (!deep_push<FAST>(k1, dsm, s, cc & 1u, x, y)) { produced = false; break; }
-          x = y;
-          cc >>= 1;
-        }
-        if (produced) {
-          if (out_pos >= out_first && active) store_p2(xd + out_pos, x);
-          out_pos++;
-        }
-        chunk_ctr++;
+      for (int i = 0; i < (kChunk >> NF); ++i) {
+        if (out_pos >= out_first && active) store_p2(mid + (size_t)out_pos * p.mid_pitch, out[i]);   // 32 lanes: one 256-byte row
+        out_pos++;
       }
+    }
+    if (FMT == FMT_CF32) {
+      __syncwarp();   // every lane has finished reading this raw slot
+      if (tid == 0 && t + TS::kRawStages < ntiles) issue(t + TS::kRawStages);
     }
   }
 
@@ -558,16 +553,126 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
 #pragma unroll
         for (int k = 0; k < 3; ++k) store_p2(hand + (size_t)(s * kStateSlots + 5 + k) * kThreads, hb[s].o[k]);
       }
-      for (int s = 0; s < ndeep; ++s)
-        for (int k = 0; k < kStateSlots; ++k) store_p2(hand + (size_t)((NF + s) * kStateSlots + k) * kThreads, dsm.at(s, k));
       hand[(size_t)(kHandSlots - 1) * kThreads] = make_float2(oa, ob);
     }
     __threadfence();
-    __syncthreads();
+    __syncwarp();
     if (tid == 0) {
       const int done = q + 1;
       asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(done) : "memory");
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deep kernel: half-band stages DA .. D-1 of every VFO of one launch group, from the stage-DA stream the main kernel
+// wrote ([time][VFO], so a warp's 32 VFOs read one 256-byte row per time step), to the per-VFO stage-D rows the
+// tail kernel reads. One warp = 32 VFOs x one range of T input samples, history in registers; ranges after the first
+// run in over Wd = 10*(2^3 - 1) (rounded to 8) earlier samples with zero history and discard those outputs; range 0
+// starts from the block's saved (shifted, see boundary_role) history. A VFO with D <= 5 has no deep stage: its
+// samples are only moved into its row. Lanes of a warp may differ in their stage count.
+// ---------------------------------------------------------------------------------------------
+struct DeepParams {
+  const float2* mid;          // [n_mid][mid_pitch]
+  const float2* state_in;     // [kMaxStages][kStateSlots][vfo_pitch]
+  float2* const* xd_rows;     // [vfo_pitch] per VFO: where stage-D sample 0 of this block goes
+  const unsigned char* vfo_D; // [vfo_pitch]
+  int vfo_pitch, mid_pitch, vfo_base, vfo_count;
+  int DA;                     // stages already done by the main kernel
+  int n_mid;                  // B >> DA
+  int T, Wd, nranges;
+  float one;
+};
+
+constexpr int kDeepWarps = 4;
+constexpr int kDeepWarm = 72;          // 10*(2^3 - 1) input samples reach the last deep stage's history; rounded up to 8
+
+template <bool FAST>
+__global__ void __launch_bounds__(32 * kDeepWarps) ddc_deep_kernel(const DeepParams p) {
+  const int lane = threadIdx.x & 31;
+  const int range = blockIdx.y * kDeepWarps + (threadIdx.x >> 5);
+  if (range >= p.nranges) return;
+  const int slot = blockIdx.x * 32 + lane;
+  const bool active = slot < p.vfo_count;
+  const int vfo = p.vfo_base + (active ? slot : 0);
+  const int D = p.vfo_D[vfo];
+  const int nd = max(D - p.DA, 0);                         // 0..3 deep stages for this VFO
+  Ones k1; k1.one = bcast2(p.one);
+  HbState hb[kDeepStages];
+  const int t0 = range * p.T;
+  const int t1 = min(t0 + p.T, p.n_mid);
+  const int ts = range == 0 ? 0 : t0 - p.Wd;
+  if (range == 0) {
+#pragma unroll
+    for (int s = 0; s < kDeepStages; ++s) {
+      const int st_i = min(p.DA + s, kMaxStages - 1);
+      const float2* st = p.state_in + (size_t)st_i * kStateSlots * p.vfo_pitch + vfo;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) hb[s].e[k] = s < nd ? load_p2(st + (size_t)k * p.vfo_pitch) : pzero();
+#pragma unroll
+      for (int k = 0; k < 3; ++k) hb[s].o[k] = s < nd ? load_p2(st + (size_t)(5 + k) * p.vfo_pitch) : pzero();
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < kDeepStages; ++s) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) hb[s].e[k] = pzero();
+#pragma unroll
+      for (int k = 0; k < 3; ++k) hb[s].o[k] = pzero();
+    }
+  }
+  float2* xd = p.xd_rows[vfo];
+  const float2* src = p.mid + (active ? slot : 0);
+  // eight input samples at a time while they last (ts and t0 are multiples of 8, so every stage starts a group on its
+  // even phase): 4 / 2 / 1 outputs of deep stage 1 / 2 / 3
+  int t = ts;
+  for (; t + 8 <= t1; t += 8) {
+    float2 in[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) in[i] = src[(size_t)(t + i) * p.mid_pitch];
+    if (nd == 0) {
+      if (active && t >= t0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xd[t + i] = in[i];
+      }
+      continue;
+    }
+    P2 y0[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y0[i] = hb_pair<FAST>(k1, hb[0], pack2(in[2 * i].x, in[2 * i].y), pack2(in[2 * i + 1].x, in[2 * i + 1].y));
+    if (nd == 1) {
+      if (active && t >= t0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) store_p2(xd + (t >> 1) + i, y0[i]);
+      }
+      continue;
+    }
+    P2 y1[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) y1[i] = hb_pair<FAST>(k1, hb[1], y0[2 * i], y0[2 * i + 1]);
+    if (nd == 2) {
+      if (active && t >= t0) {
+        store_p2(xd + (t >> 2), y1[0]);
+        store_p2(xd + (t >> 2) + 1, y1[1]);
+      }
+      continue;
+    }
+    const P2 y2 = hb_pair<FAST>(k1, hb[2], y1[0], y1[1]);
+    if (active && t >= t0) store_p2(xd + (t >> 3), y2);
+  }
+  // the last range of a stream whose length is not a multiple of 8 (then no VFO has 3 deep stages): sample by sample
+  for (; t < t1; ++t) {
+    P2 x = load_p2(src + (size_t)t * p.mid_pitch);
+    int cnt = t;
+    bool stop = false;
+#pragma unroll
+    for (int s = 0; s < kDeepStages; ++s) {
+      if (!stop && s < nd) {
+        if (cnt & 1) { hb_odd(hb[s], x); stop = true; }
+        else { x = hb_even<FAST>(k1, hb[s], x); cnt >>= 1; }
+      }
+    }
+    if (!stop && active && t >= t0) store_p2(xd + (t >> nd), x);
   }
 }
 

@@ -1,5 +1,11 @@
-// aero-ddc-b200: the fleet object of include/aeroddc.h - one aeroddc_bank per GPU, VFOs sharded over them, the raw
-// block broadcast with NCCL. Host orchestration only; all arithmetic is the banks'.
+// aero-ddc-b200: the fleet object of include/aeroddc.h - one aeroddc_bank per GPU, VFOs sharded over them (SURVEY.md
+// section 8e). Host orchestration only; all arithmetic is the banks'.
+// Exchange of the raw block, two ways:
+//   peer (default)  every GPU ingests 1/N of the block over its OWN PCIe link (N concurrent H2D copies); every bank's
+//                   main kernel then pulls each raw tile from the GPU that holds it with its TMA loads (peer memory over
+//                   NVLink, aeroddc_bank_submit_device_sliced) - the exchange is fused into the compute, tile by tile.
+//   nccl            the whole block goes to devices[0] and is broadcast with ncclBroadcast (AERODDC_EXCHANGE=nccl, or
+//                   when the GPUs cannot map each other's memory).
 #include "../../include/aeroddc.h"
 
 #include <cuda_runtime.h>
@@ -7,6 +13,8 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -77,11 +85,15 @@ struct aeroddc_fleet {
   bool finalized = false;
   size_t in_bytes = 0;
   std::vector<ncclComm_t> comms;
-  std::vector<cudaStream_t> streams;            // per device: carries the broadcast
-  std::vector<unsigned char*> d_in[2];          // per device raw block, two parities
-  std::vector<cudaEvent_t> ev_ready[2];         // per device: block of parity p has arrived
+  std::vector<cudaStream_t> streams;            // per device: carries the H2D of its slice / the broadcast
+  std::vector<unsigned char*> d_in[2];          // per device, two parities: its slice of the raw block (peer) or the whole block (nccl)
+  std::vector<cudaEvent_t> ev_ready[2];         // per device: its buffer of parity p has arrived
   void* h_slot[2] = {nullptr, nullptr};
   long long submitted = 0, done = 0;
+  bool peer = false;                            // exchange mode
+  size_t slice_len = 0;                         // complex samples per slice (peer mode)
+  int n_slices = 1;
+  bool failed = false;                          // a bank reported an error: the fleet is out of step and refuses further work
 };
 
 extern "C" {
@@ -152,18 +164,36 @@ int aeroddc_fleet_finalize(aeroddc_fleet* f) {
   size_t bytes = 0;
   FOK(aeroddc_bank_host_slot(f->banks[0], 0, &f->h_slot[0], &bytes));
   FOK(aeroddc_bank_host_slot(f->banks[0], 1, &f->h_slot[1], &bytes));
+  const int bps = f->fmt == AERODDC_CU8 ? 2 : (f->fmt == AERODDC_CS16 ? 4 : 8);
   if (nd > 1) {
-    if (!nccl().ok) return aeroddc_set_error(AERODDC_ERR_CUDA, "libnccl.so.2 not found: a fleet of %d GPUs needs NCCL for the raw-block broadcast", nd);
-    f->comms.resize(nd);
-    FNC(nccl().CommInitAll(f->comms.data(), nd, f->devices.data()));
+    const char* mode = getenv("AERODDC_EXCHANGE");
+    f->peer = !(mode && strcmp(mode, "nccl") == 0);
+    if (f->peer) {   // every GPU must be able to map every other GPU's memory
+      for (int i = 0; i < nd && f->peer; ++i)
+        for (int j = 0; j < nd && f->peer; ++j)
+          if (i != j && aeroddc_enable_peer(f->devices[i], f->devices[j]) != AERODDC_OK) f->peer = false;
+    }
+    if (f->peer) {
+      // equal slices, a multiple of 256 samples (one raw tile) so that almost no tile straddles two GPUs
+      size_t sl = ((size_t)f->B + nd - 1) / nd;
+      sl = (sl + 255) / 256 * 256;
+      f->slice_len = sl;
+      f->n_slices = (int)(((size_t)f->B + sl - 1) / sl);
+      if (f->n_slices < 2) f->peer = false;   // a block too short to share out: fall through to the broadcast
+    }
+    if (!f->peer) {
+      if (!nccl().ok) return aeroddc_set_error(AERODDC_ERR_CUDA, "libnccl.so.2 not found: this fleet of %d GPUs needs NCCL for the raw-block broadcast", nd);
+      f->comms.resize(nd);
+      FNC(nccl().CommInitAll(f->comms.data(), nd, f->devices.data()));
+    }
   }
   f->streams.resize(nd);
-  for (int p = 0; p < 2; ++p) { f->d_in[p].resize(nd); f->ev_ready[p].resize(nd); }
+  for (int p = 0; p < 2; ++p) { f->d_in[p].assign(nd, nullptr); f->ev_ready[p].assign(nd, nullptr); }
   for (int i = 0; i < nd; ++i) {
     FCU(cudaSetDevice(f->devices[i]));
     FCU(cudaStreamCreateWithFlags(&f->streams[i], cudaStreamNonBlocking));
     for (int p = 0; p < 2; ++p) {
-      FCU(cudaMalloc((void**)&f->d_in[p][i], f->in_bytes));
+      if (nd > 1 && (!f->peer || i < f->n_slices)) FCU(cudaMalloc((void**)&f->d_in[p][i], f->peer ? f->slice_len * bps : f->in_bytes));
       FCU(cudaEventCreateWithFlags(&f->ev_ready[p][i], cudaEventDisableTiming));
     }
   }
@@ -182,30 +212,56 @@ int aeroddc_fleet_host_slot(aeroddc_fleet* f, int slot, void** ptr, size_t* byte
 int aeroddc_fleet_submit(aeroddc_fleet* f, const void* host_iq, size_t n_complex) {
   if (!f || !host_iq) return aeroddc_set_error(AERODDC_ERR_ARG, "NULL argument");
   if (!f->finalized) return aeroddc_set_error(AERODDC_ERR_STATE, "fleet not finalized");
+  if (f->failed) return aeroddc_set_error(AERODDC_ERR_STATE, "the fleet stopped after an earlier error; destroy it");
   if (n_complex != (size_t)f->B) return aeroddc_set_error(AERODDC_ERR_ARG, "block of %zu samples, fleet was created for %d", n_complex, f->B);
   if (f->submitted - f->done >= 2) return aeroddc_set_error(AERODDC_ERR_STATE, "two blocks already in flight; call wait()");
   const int nd = (int)f->banks.size();
+  if (nd == 1) {   // one GPU: the bank's own pinned ring and copy stream
+    FOK(aeroddc_bank_submit(f->banks[0], host_iq, n_complex));
+    f->submitted++;
+    return AERODDC_OK;
+  }
   const int p = (int)(f->submitted & 1);
-  const void* src = host_iq;
+  const unsigned char* src = (const unsigned char*)host_iq;
   if (host_iq != f->h_slot[0] && host_iq != f->h_slot[1]) {   // pageable caller memory: stage through the pinned ring
     memcpy(f->h_slot[p], host_iq, f->in_bytes);
-    src = f->h_slot[p];
+    src = (const unsigned char*)f->h_slot[p];
   }
   // the buffers of parity p were last read by the block submitted two calls ago; the in-flight limit above means
-  // wait() has retired it (payload copied out, hence kernels done), so no event is needed before overwriting them
-  FCU(cudaSetDevice(f->devices[0]));
-  FCU(cudaMemcpyAsync(f->d_in[p][0], src, f->in_bytes, cudaMemcpyHostToDevice, f->streams[0]));
-  if (nd > 1) {
+  // wait() has retired it on every GPU (payload copied out, hence kernels done), so no event is needed before overwriting them
+  int rc = AERODDC_OK;
+  if (f->peer) {
+    const size_t bps = f->in_bytes / (size_t)f->B;
+    std::vector<const void*> slices(f->n_slices);
+    std::vector<void*> events(f->n_slices);
+    for (int i = 0; i < f->n_slices; ++i) {   // N concurrent uploads, one per GPU and PCIe link
+      const size_t off = (size_t)i * f->slice_len;
+      const size_t cnt = std::min(f->slice_len, (size_t)f->B - off);
+      FCU(cudaSetDevice(f->devices[i]));
+      FCU(cudaMemcpyAsync(f->d_in[p][i], src + off * bps, cnt * bps, cudaMemcpyHostToDevice, f->streams[i]));
+      FCU(cudaEventRecord(f->ev_ready[p][i], f->streams[i]));
+      slices[i] = f->d_in[p][i];
+      events[i] = f->ev_ready[p][i];
+    }
+    for (int i = 0; i < nd; ++i) {   // every bank reads all slices in place, across NVLink
+      const int r = aeroddc_bank_submit_device_sliced(f->banks[i], slices.data(), f->n_slices, f->slice_len, n_complex, events.data(), f->n_slices);
+      if (r != AERODDC_OK && rc == AERODDC_OK) rc = r;
+    }
+  } else {
+    FCU(cudaSetDevice(f->devices[0]));
+    FCU(cudaMemcpyAsync(f->d_in[p][0], src, f->in_bytes, cudaMemcpyHostToDevice, f->streams[0]));
     FNC(nccl().GroupStart());
     for (int i = 0; i < nd; ++i)
       FNC(nccl().Broadcast(f->d_in[p][0], f->d_in[p][i], f->in_bytes, kNcclUint8, 0, f->comms[i], f->streams[i]));
     FNC(nccl().GroupEnd());
+    for (int i = 0; i < nd; ++i) {
+      FCU(cudaSetDevice(f->devices[i]));
+      FCU(cudaEventRecord(f->ev_ready[p][i], f->streams[i]));
+      const int r = aeroddc_bank_submit_device(f->banks[i], f->d_in[p][i], n_complex, f->ev_ready[p][i]);
+      if (r != AERODDC_OK && rc == AERODDC_OK) rc = r;
+    }
   }
-  for (int i = 0; i < nd; ++i) {
-    FCU(cudaSetDevice(f->devices[i]));
-    FCU(cudaEventRecord(f->ev_ready[p][i], f->streams[i]));
-    FOK(aeroddc_bank_submit_device(f->banks[i], f->d_in[p][i], n_complex, f->ev_ready[p][i]));
-  }
+  if (rc != AERODDC_OK) { f->failed = true; return rc; }   // some banks took the block and some did not: out of step for good
   f->submitted++;
   return AERODDC_OK;
 }
@@ -213,8 +269,23 @@ int aeroddc_fleet_submit(aeroddc_fleet* f, const void* host_iq, size_t n_complex
 int aeroddc_fleet_wait(aeroddc_fleet* f) {
   if (!f) return aeroddc_set_error(AERODDC_ERR_ARG, "NULL fleet");
   if (f->done >= f->submitted) return aeroddc_set_error(AERODDC_ERR_STATE, "nothing in flight");
-  for (aeroddc_bank* b : f->banks) FOK(aeroddc_bank_wait(b));
+  // retire the block on EVERY bank, whatever the first one says, so that the banks stay in step with each other
+  int rc = AERODDC_OK;
+  std::string first_msg;
+  for (aeroddc_bank* b : f->banks) {
+    const int r = aeroddc_bank_wait(b);
+    if (r != AERODDC_OK && rc == AERODDC_OK) { rc = r; first_msg = aeroddc_last_error(); }
+  }
   f->done++;
+  if (rc != AERODDC_OK) { f->failed = true; return aeroddc_set_error(rc, "%s", first_msg.c_str()); }
+  return AERODDC_OK;
+}
+
+int aeroddc_fleet_reset(aeroddc_fleet* f) {
+  if (!f) return aeroddc_set_error(AERODDC_ERR_ARG, "NULL fleet");
+  if (f->done != f->submitted) return aeroddc_set_error(AERODDC_ERR_STATE, "blocks in flight; call wait() first");
+  for (aeroddc_bank* b : f->banks) FOK(aeroddc_bank_reset(b));
+  f->submitted = f->done = 0;
   return AERODDC_OK;
 }
 
@@ -230,6 +301,7 @@ int aeroddc_fleet_output(aeroddc_fleet* f, int vfo, const void** payload, size_t
 }
 
 int aeroddc_fleet_num_devices(aeroddc_fleet* f) { return f ? (int)f->banks.size() : 0; }
+int aeroddc_fleet_exchange(aeroddc_fleet* f) { return !f || f->banks.size() < 2 ? 0 : (f->peer ? 1 : 2); }
 int aeroddc_fleet_device_of(aeroddc_fleet* f, int vfo) {
   if (!f || vfo < 0 || vfo >= (int)f->where.size()) return -1;
   return f->where[vfo].dev;
@@ -249,6 +321,11 @@ int aeroddc_dev_free(int device, void* dev_ptr) {
 int aeroddc_dev_upload(int device, void* dev_ptr, const void* host, size_t bytes) {
   FCU(cudaSetDevice(device));
   FCU(cudaMemcpy(dev_ptr, host, bytes, cudaMemcpyHostToDevice));
+  return AERODDC_OK;
+}
+int aeroddc_dev_upload_async(int device, void* dev_ptr, const void* pinned_host, size_t bytes, void* stream) {
+  FCU(cudaSetDevice(device));
+  FCU(cudaMemcpyAsync(dev_ptr, pinned_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
   return AERODDC_OK;
 }
 int aeroddc_ipc_export(int device, void* dev_ptr, unsigned char handle[AERODDC_IPC_HANDLE_BYTES]) {

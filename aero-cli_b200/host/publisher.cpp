@@ -41,6 +41,8 @@ Publisher::Publisher(const std::string& deviceStr, bool enableBiast_, bool enabl
     for (vfo* m : VFOmain) m->addToBank(bank, -1);
     for (vfo* f : VFOflat) f->addToBank(bank, -1);
     bank->finalize();
+    for (vfo* m : VFOmain) m->connectSockets();   // the socket half of vfo::init; throws when there is no way to publish
+    for (vfo* f : VFOflat) f->connectSockets();
   } catch (const std::exception& e) {
     error = e.what();
     CRIT("[ERROR] %s", e.what());

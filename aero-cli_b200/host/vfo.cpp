@@ -48,6 +48,7 @@ vfo::vfo() {   // defaults of vfo::vfo (vfo.cpp:5-29); Fs / decimateCount / mixe
   samplesPerBuffer_ = 0;
   lateDecimate_ = 0;
   inited_ = false;
+  socketsReady_ = false;
   index_ = -1;
 }
 
@@ -63,17 +64,33 @@ void vfo::init(int samplesPerBuffer, bool bind, int lateDecimate) {
   int targetRate = (int)(Fs / std::pow(2.0, decimateCount));
   if (demodUSB && lateDecimate > 0) targetRate = targetRate / lateDecimate;
   outputRate = (uint32_t)targetRate;
-  if (!vfo::bind_publisher.connected && bind) {   // vfo.cpp:128-136
-    vfo::bind_publisher.setAddress(zmqAddress);
-    vfo::bind_publisher.setBind(bind);
-    vfo::bind_publisher.connect();
-  } else if (!bind) {
+  zmqBind = bind;   // the sockets themselves are opened by connectSockets(), not while settings are being parsed
+  inited_ = true;
+}
+
+// The socket part of vfo::init (vfo.cpp:128-136), deferred until the VFO is about to run: parsing a settings file
+// (aero-publish-b200 --plan) must not bind the publisher's address. Only VFOs that can publish open a socket: a main VFO
+// that feeds sub-VFOs never sends (vfo.cpp:167-172), and IQ output needs a topic (vfo.cpp:300).
+void vfo::connectSockets() {
+  if (mpVFOs && !mpVFOs->empty()) {
+    for (vfo* s : *mpVFOs) s->connectSockets();
+    return;
+  }
+  if (socketsReady_ || (!demodUSB && zmqTopic.empty())) return;
+  if (!ZmqPublisher::available())
+    throw std::runtime_error("ZeroMQ output unavailable: libzmq could not be loaded (set AERODDC_LIBZMQ to its path) and no sink is installed");
+  if (zmqBind) {
+    if (!vfo::bind_publisher.connected) {
+      vfo::bind_publisher.setAddress(zmqAddress);
+      vfo::bind_publisher.setBind(true);
+      vfo::bind_publisher.connect();
+    }
+  } else {
     connect_publisher.setBind(false);
     connect_publisher.setAddress(zmqAddress);
     connect_publisher.connect();
   }
-  zmqBind = bind;
-  inited_ = true;
+  socketsReady_ = true;
 }
 
 void vfo::setZmqAddress(const std::string& address) { zmqAddress = address; }
@@ -138,6 +155,7 @@ void vfo::transmitData() {
   if (aeroddc_fleet_output(bank_->handle(), index_, &payload, &n, &rate) != AERODDC_OK)
     throw std::runtime_error(std::string("aeroddc_fleet_output: ") + aeroddc_last_error());
   if (!demodUSB && zmqTopic.empty()) return;   // vfo.cpp:300: IQ is only sent when a topic is set
+  connectSockets();                             // first message of a VFO driven on its own; a no-op afterwards
   ZmqPublisher& pub = zmqBind ? vfo::bind_publisher : connect_publisher;
   pub.publish((unsigned char*)payload, (uint32_t)n, zmqTopic, rate);
 }

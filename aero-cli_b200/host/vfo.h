@@ -3,7 +3,8 @@
 // against the reference's class read the same here; the arithmetic runs in libaeroddc.so on the GPU.
 //
 // Differences that follow from batching every VFO into one GPU bank:
-//  * init() only records the configuration. The bank is built lazily: by Publisher for all VFOs of a
+//  * init() only records the configuration (and opens no socket: connectSockets() does, when the VFO is about to run,
+//    so that parsing a settings file with --plan binds nothing). The bank is built lazily: by Publisher for all VFOs of a
 //    settings file (Publisher::start), or - for a vfo driven on its own like the reference's object -
 //    at its first process() call, together with the sub-VFOs attached by setVFOs().
 //  * process() on a main VFO processes its sub-VFOs in the same GPU pass (the reference recurses,
@@ -75,6 +76,9 @@ class vfo {
   void addToBank(const std::shared_ptr<aero::DdcBank>& bank, int parent);
   // hand the last completed block's payload to ZmqPublisher (vfo::transmitData); recurses into sub-VFOs
   void transmitData();
+  // open the ZeroMQ socket(s) this VFO and its sub-VFOs publish on (the socket half of vfo::init, vfo.cpp:128-136);
+  // throws std::runtime_error when neither libzmq nor a sink is available - messages are never dropped silently
+  void connectSockets();
   int bankIndex() const { return index_; }
   int samplesPerBuffer() const { return samplesPerBuffer_; }
   int lateDecimate() const { return lateDecimate_; }
@@ -99,7 +103,7 @@ class vfo {
   int filterbw, offsetbw;
   int scalecomp;
   int samplesPerBuffer_, lateDecimate_;
-  bool inited_;
+  bool inited_, socketsReady_;
   std::shared_ptr<aero::DdcBank> bank_;
   int index_;
 };

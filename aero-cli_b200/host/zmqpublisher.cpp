@@ -1,8 +1,8 @@
 #include "zmqpublisher.h"
 
 #include <dlfcn.h>
-#include <glob.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -30,16 +30,7 @@ ZmqApi& api() {
     if (const char* env = getenv("AERODDC_LIBZMQ")) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
     for (const char* name : {"libzmq.so.5", "libzmq.so"})
       if (!h) h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
-    if (!h) {   // pyzmq wheels bundle libzmq under site-packages/pyzmq.libs/
-      glob_t g;
-      for (const char* pat : {"/opt/*/.venv/lib/python3*/site-packages/pyzmq.libs/libzmq*.so*", "/usr/lib/python3*/site-packages/pyzmq.libs/libzmq*.so*"}) {
-        if (!h && glob(pat, 0, nullptr, &g) == 0) {
-          for (size_t i = 0; i < g.gl_pathc && !h; ++i) h = dlopen(g.gl_pathv[i], RTLD_NOW | RTLD_GLOBAL);
-          globfree(&g);
-        }
-      }
-    }
-    if (!h) return;
+    if (!h) return;   // no search beyond the loader path: AERODDC_LIBZMQ names a library living elsewhere (e.g. pyzmq's bundled copy)
     a.ctx_new = (void* (*)())dlsym(h, "zmq_ctx_new");
     a.socket = (void* (*)(void*, int))dlsym(h, "zmq_socket");
     a.setsockopt = (int (*)(void*, int, const void*, size_t))dlsym(h, "zmq_setsockopt");
@@ -57,10 +48,20 @@ void ZmqPublisher::setSink(Sink sink) { g_sink = std::move(sink); }
 
 ZmqPublisher::ZmqPublisher() : connected(false), context(nullptr), publisher(nullptr), bindAddress("tcp://*:6002"), zmqStatus(0), bind(false) {}
 
+bool ZmqPublisher::available() { return g_sink || api().ok; }
+
 void ZmqPublisher::connect() {
   if (connected) return;
-  if (g_sink || !api().ok) {   // no socket: messages go to the sink (or are dropped, as the reference drops them on a failed bind)
+  if (g_sink) {   // test / replay hook installed: no socket, every message goes to the sink
     connected = true;
+    return;
+  }
+  if (!api().ok) {
+    // The reference links libzmq at build time, so this cannot happen there. Here it must not pass silently: the publisher
+    // stays unconnected, the caller (vfo / Publisher) turns that into an error, and nothing is ever "published" into the void.
+    static bool said = false;
+    if (!said) fprintf(stderr, "[CRIT] libzmq could not be loaded (tried $AERODDC_LIBZMQ, libzmq.so.5, libzmq.so): no ZeroMQ output possible\n");
+    said = true;
     return;
   }
   ZmqApi& z = api();

@@ -8,16 +8,24 @@ Workload (BASELINE.json configs[3], the one the metric is quoted on; it fits one
 at integer-Hz offsets within +-0.45 Fs over ONE synthetic 61.44 MS/s cf32 stream, D = 8 half-band
 stages + late /5 FIR -> 48 kHz USB-demodulated int16 per VFO. A step is one block of
 B = Fs/4 = 15 360 000 complex samples (the reference's block contract) through the whole chain for
-all V VFOs. With N GPUs the VFOs are sharded v mod N (strong scaling: total work fixed), the raw
-block is broadcast from rank 0 with NCCL, and every rank returns its own payloads to its host.
+all V VFOs. With N GPUs the VFOs are sharded v mod N (strong scaling: total work fixed); the raw block
+is spread over the GPUs in N slices (each GPU ingests 1/N over its own PCIe link) and every GPU's kernel
+pulls the raw tiles from the slice that holds them over NVLink (peer memory, fused with the compute);
+`--exchange nccl` broadcasts the block from rank 0 with NCCL instead. Every rank returns its own payloads.
 
 metric / value : aggregate VFO-channel input samples/s = V * B * K / device time, Gsps, raw blocks
-                 resident in HBM (rank 0's HBM for N > 1; the NCCL broadcast is inside the region),
-                 two alternating 123 MB input buffers (larger than the 126 MB L2 together).
-e2e            : the same through the host-facing C-ABI calls (aeroddc_bank_submit/wait): pinned
-                 host blocks, H2D copy of every block and D2H of every payload inside the region.
-roofline       : the dominant kernel (ddc_main_kernel: unpack + NCO mix + half-band cascade) against
+                 resident in HBM (two alternating 123 MB blocks, larger than the 126 MB L2 together).
+e2e            : the same through the host-facing calls: pinned host blocks, H2D copy of every block
+                 and D2H of every payload inside the region.
+roofline       : the dominant kernel (ddc_main_kernel: unpack + NCO mix + half-band stages 0-4) against
                  the FP32 FFMA issue peak measured in the same run (aeroddc_measure_fp32_peak).
+parity         : after the timed regions the SAME bank is rewound and fed six consecutive distinct blocks
+                 (five block boundaries and the oscillator-table wrap at sample Fs) through the same
+                 device path; the payloads of the first and last VFO of this rank's shard and six others
+                 are compared byte for byte with the unmodified reference chain (oracle/_ref).
+configs        : (N = 1) side lines for BASELINE configs[0..2]: 1 VFO at 2.4 MS/s cu8, the 30-VFO
+                 ini-style bank at 1.536 MS/s cu8, 256 VFOs at 61.44 MS/s; and the main configuration
+                 with DC correction on.
 cpu_baseline   : the reference's own vfo::process chain (oracle/_ref, or the oracle port) on the
                  host cores, one VFO per thread, bounded sample.
 --impl reference prints the CPU figure as the headline line instead.
@@ -39,11 +47,21 @@ FS = 61440000
 BLOCK = FS // 4
 DECIM, LATE, GAIN = 8, 5, 0.05
 N_VFOS = 1024
-# algorithmic flops per VFO-input-sample (mul and add each 1 flop):
-# mix 6 + half-band cascade 20*(1 - 2^-D); tail (late FIR 4*49/5 + Hilbert/delay/convert 253/5)/2^D
-FLOPS_MAIN = 6.0 + 20.0 * (1.0 - 2.0 ** -DECIM)
-FLOPS_TAIL = ((4 * 49) / 5.0 + 253 / 5.0) / 2.0 ** DECIM
-FLOPS_TOTAL = FLOPS_MAIN + FLOPS_TAIL
+PARITY_BLOCKS = 6
+
+
+def flops_per_sample(D, late, usb_taps=0, late_taps=49):
+    """Algorithmic flops per VFO-input-sample (mul and add each 1 flop):
+    (main kernel: mix 6 + half-band stages 0..min(D,5)-1, deep kernel: stages 5..D-1, tail)."""
+    da = min(D, 5)
+    main = 6.0 + 20.0 * (1.0 - 2.0 ** -da)
+    deep = 20.0 * (2.0 ** -da - 2.0 ** -D)
+    tail = ((4.0 * late_taps / late if late else 0.0) + (250 + 1 + 2 * usb_taps + 2) / max(late, 1)) / 2.0 ** D
+    return main, deep, tail
+
+
+FLOPS_MAIN, FLOPS_DEEP, FLOPS_TAIL = flops_per_sample(DECIM, LATE)
+FLOPS_TOTAL = FLOPS_MAIN + FLOPS_DEEP + FLOPS_TAIL
 
 
 def vfo_freqs(n):
@@ -63,6 +81,12 @@ def synth_block(seed):
     return x
 
 
+def parity_block(k, n=BLOCK):
+    """Block k of the parity sequence: full-scale uniform noise (every rank regenerates the same bytes)."""
+    rng = np.random.default_rng(7000 + k)
+    return (rng.random(2 * n, dtype=np.float32) * np.float32(1.9) - np.float32(0.95))
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -76,7 +100,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -114,30 +138,47 @@ class ClockSampler:
         thr = 0.6 * max(pw)
         load = [s for s, p in zip(sm, pw) if p >= thr] or sm
         return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_under_load": len(load), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side (the checker; oracle/ is touched here, in parity_check() and nowhere else)
+# ------------------------------------------------------------------------------------------------
+def _oracle_bind():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_bind as ob
+    return ob
 
 
 class CpuChain:
     """Reference CPU chain, one `vfo` object per host thread (BASELINE.md plan (ii)).
     Objects (and their 491 MB oscillator tables) are built once, outside any timed region."""
 
-    def __init__(self, n_threads):
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import oracle_bind as ob
-
+    def __init__(self, n_threads, fs=FS, blk=BLOCK, chains=None):
+        ob = _oracle_bind()
         self.kind = "reference" if ob.ref_lib() is not None else "port"
-        self.n = n_threads
         cls = ob.RefVfo if self.kind == "reference" else ob.Oracle
-        self.objs = [cls(FS, BLOCK, DECIM, LATE, float(f), GAIN) for f in vfo_freqs(n_threads)]
+        self.blk = blk
+        if chains is None:
+            chains = [(DECIM, LATE, float(f), GAIN) for f in vfo_freqs(n_threads)]
+        self.n = len(chains)
+        self.objs = [cls(fs, blk, d, l, f, g) for (d, l, f, g) in chains]
 
     def single(self, x):
         t0 = time.perf_counter()
         self.objs[0].process_repeat(x, 1)
-        return BLOCK / (time.perf_counter() - t0) / 1e9
+        return self.blk / (time.perf_counter() - t0) / 1e9
 
-    def step(self, x, blocks_per_vfo=1):
-        """All threads process `blocks_per_vfo` blocks; returns wall seconds."""
-        ths = [threading.Thread(target=o.process_repeat, args=(x, blocks_per_vfo)) for o in self.objs]
+    def step(self, x, blocks_per_vfo=1, n_threads=None):
+        """Every object processes `blocks_per_vfo` blocks, spread over n_threads host threads; returns wall seconds."""
+        n_threads = n_threads or len(self.objs)
+        lanes = [self.objs[i::n_threads] for i in range(n_threads)]
+
+        def work(objs):
+            for o in objs:
+                o.process_repeat(x, blocks_per_vfo)
+
+        ths = [threading.Thread(target=work, args=(l,)) for l in lanes if l]
         t0 = time.perf_counter()
         for t in ths:
             t.start()
@@ -147,7 +188,7 @@ class CpuChain:
 
     def sample_text(self, blocks):
         return ("%d VFOs (one per host thread) x %d blocks of %d samples, Fs 61.44 MS/s, D=8, late /5; table build untimed"
-                % (self.n, blocks, BLOCK))
+                % (self.n, blocks, self.blk))
 
     def close(self):
         for o in self.objs:
@@ -164,6 +205,35 @@ def cpu_baseline(x):
     chain.close()
     return {"value": cores * blocks * BLOCK / dt / 1e9, "unit": "Gsps", "cores": cores, "kind": chain.kind,
             "single_thread_gsps": single, "sample": chain.sample_text(blocks)}
+
+
+def parity_check(blocks, vfo_cfgs, gpu_payloads, fs=FS, blk=BLOCK):
+    """blocks: list of host cf32 blocks; vfo_cfgs: [(D, L, f, gain)]; gpu_payloads[i][k] = bytes of VFO i, block k.
+    Runs the unmodified reference chain (oracle/_ref; the oracle port where it was never built), one VFO per host
+    thread (the harness keeps one message sink per thread). Returns (kind, [(vfo, block) that differ])."""
+    ob = _oracle_bind()
+    kind = "reference" if ob.ref_lib() is not None else "port"
+    bad = []
+
+    def one(i):
+        d, l, f, g = vfo_cfgs[i]
+        if kind == "reference":
+            topic = "P%04d" % i
+            o = ob.RefVfo(fs, blk, d, l, f, g, topic=topic)
+        else:
+            o = ob.Oracle(fs, blk, d, l, f, g)
+        for k, x in enumerate(blocks):
+            want = o.process(x)[topic][1] if kind == "reference" else o.process(x)
+            if want != gpu_payloads[i][k]:
+                bad.append((i, k))
+        o.close()
+
+    ths = [threading.Thread(target=one, args=(i,)) for i in range(len(vfo_cfgs))]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    return kind, sorted(bad)
 
 
 def run_reference(args, rank, world):
@@ -192,6 +262,125 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------
+# side configurations (BASELINE configs[0..2]) - single GPU
+# ------------------------------------------------------------------------------------------------
+def _timed_device_loop(bank, dev_ptrs, steps, warmup):
+    """steps blocks alternating over dev_ptrs, two in flight; returns (region ms, mean main-kernel ms, launches per step)."""
+    def loop(n, main_ms=None):
+        inflight = 0
+        for k in range(n):
+            if inflight == 2:
+                bank.wait(); inflight -= 1
+                if main_ms is not None:
+                    main_ms.append(bank.last_main_ms())
+            bank.submit_device(dev_ptrs[k % len(dev_ptrs)], None)
+            inflight += 1
+        while inflight:
+            bank.wait(); inflight -= 1
+            if main_ms is not None:
+                main_ms.append(bank.last_main_ms())
+    loop(warmup)
+    mm = []
+    bank.stopwatch_start(False)
+    loop(steps, mm)
+    ms = bank.stopwatch_stop()
+    return ms, float(np.mean(mm)), bank.last_timing()[1]
+
+
+def side_configs(aeroddc, torch, dev, local_rank, peak_tflops, cpu_all_core_61m):
+    """BASELINE configs[0] (1 VFO, 2.4 MS/s cu8), [1] (30-VFO ini-style bank, 1.536 MS/s cu8, one main VFO feeding 30
+    sub-VFOs as the reference requires, publisher.cpp:301-305) and [2] (256 VFOs at 61.44 MS/s cf32)."""
+    ob = _oracle_bind()
+    out = {}
+    cores = os.cpu_count() or 1
+
+    def device_blocks(arrs):
+        ts = [torch.from_numpy(a).to(dev) for a in arrs]
+        torch.cuda.synchronize()
+        return ts
+
+    # ---- A: one VFO, C-band 10500 bps channel shape, 2.4 MS/s cu8 ----
+    fs, blk = 2400000, 480000
+    bank = aeroddc.Bank(fs, blk, aeroddc.CU8, local_rank)
+    bank.add_vfo(123456.0, 5, 0, 0, 0.05, 1, 1, 1, "A0000")
+    bank.finalize()
+    raws = [ob.synth_raw(ob.FMT_CU8, k * blk, blk, seed=11, amp=0.5) for k in range(2)]
+    ts = device_blocks(raws)
+    steps = 200
+    ms, mm, launches = _timed_device_loop(bank, [t.data_ptr() for t in ts], steps, 5)
+    bank.close()
+    fm, fd, ft = flops_per_sample(5, 0)
+    gs = blk * steps / (ms * 1e-3) / 1e9
+    xf = ob.unpack(ob.FMT_CU8, raws[0])
+    c = CpuChain(1, fs, blk, [(5, 0, 123456.0, 0.05)])
+    c.step(xf, 1)
+    nb = 40
+    dt = c.step(xf, nb)
+    c.close()
+    out["A"] = {"workload": "1 VFO, 2.4 MS/s cu8, D=5 -> 75 kHz USB int16 (BASELINE configs[0]); step = one block of %d samples" % blk,
+                "value": gs, "unit": "Gsps", "ms_per_step": ms / steps, "realtime_x": gs * 1e9 / fs, "launches_per_step": launches,
+                "roofline_frac_fp32": gs * 1e9 * (fm + fd + ft) / 1e12 / peak_tflops,
+                "cpu": {"value": nb * blk / dt / 1e9, "unit": "Gsps", "cores": 1, "kind": c.kind, "sample": "%d blocks; one VFO cannot use more than one thread" % nb},
+                "note": "one VFO uses one lane of each 32-lane warp; the figure is set by latency, not by the FP32 pipe"}
+
+    # ---- B: ini-style bank ----
+    fs, blk = 1536000, 384000
+    rng = np.random.default_rng(54)
+    ds = [7] * 20 + [6] * 8 + [5] * 2
+    fr = rng.integers(int(-0.45 * fs), int(0.45 * fs), 30).astype(np.float64)
+    gains = rng.integers(5, 11, 30) / 100.0
+    bank = aeroddc.Bank(fs, blk, aeroddc.CU8, local_rank)
+    main = bank.add_vfo(0.0, 0, 0, 0, 0.01, 0, 1, 1, "MAIN0")
+    for i in range(30):
+        bank.add_vfo(float(fr[i]), ds[i], 0, 0, float(gains[i]), 1, 1, 1, "B%04d" % i, parent=main)
+    bank.finalize()
+    raws = [ob.synth_raw(ob.FMT_CU8, k * blk, blk, seed=12, amp=0.5) for k in range(2)]
+    ts = device_blocks(raws)
+    steps = 200
+    ms, mm, launches = _timed_device_loop(bank, [t.data_ptr() for t in ts], steps, 5)
+    bank.close()
+    gs = 30 * blk * steps / (ms * 1e-3) / 1e9
+    fl = 6.0 + sum(sum(flops_per_sample(d, 0)) for d in ds)          # main VFO: mix only; per input sample of the stream
+    xf = ob.unpack(ob.FMT_CU8, raws[0])
+    mainc = CpuChain(1, fs, blk, [(0, 0, 0.0, 0.01)])
+    # the main VFO's stream is the sub-VFOs' input (vfo.cpp:167-172); it is an IQ-output VFO in the reference, here its
+    # USB twin stands in for timing only (same mix loop, no half-band stage)
+    subs = CpuChain(30, fs, blk, [(ds[i], 0, float(fr[i]), float(gains[i])) for i in range(30)])
+    nb = 4
+    t_main = mainc.step(xf, nb)
+    subs.step(xf, 1, n_threads=min(cores, 30))
+    t_subs = subs.step(xf, nb, n_threads=min(cores, 30))
+    t_one = subs.step(xf, 1, n_threads=1)
+    mainc.close(); subs.close()
+    out["B"] = {"workload": "sdr_54W_all.ini-style bank: 1 main VFO (D=0) feeding 30 sub-VFOs (20 x D=7, 8 x D=6, 2 x D=5 -> 12/24/48 kHz USB int16), 1.536 MS/s cu8 (BASELINE configs[1]); step = one block of %d samples; value counts the 30 publishing channels" % blk,
+                "value": gs, "unit": "Gsps", "ms_per_step": ms / steps, "realtime_x": gs * 1e9 / (30 * fs), "launches_per_step": launches,
+                "roofline_frac_fp32": (blk * steps / (ms * 1e-3)) * fl / 1e12 / peak_tflops,
+                "cpu": {"value": 30 * blk * nb / (t_main + t_subs) / 1e9, "unit": "Gsps", "cores": min(cores, 30), "kind": subs.kind,
+                        "single_thread_gsps": 30 * blk / (t_main / nb + t_one) / 1e9,
+                        "sample": "%d blocks: main VFO mix on one thread, then the 30 sub-VFO chains over %d threads" % (nb, min(cores, 30))},
+                "note": "31 VFOs fill 1 + 1 warps; kernel launches and latency, not the FP32 pipe, set the figure"}
+
+    # ---- C: 256 VFOs, wideband ----
+    freqs = vfo_freqs(N_VFOS)[:256]
+    bank = aeroddc.Bank(FS, BLOCK, aeroddc.CF32, local_rank)
+    for v in range(256):
+        bank.add_vfo(float(freqs[v]), DECIM, LATE, 0, GAIN, 1, 1, 1, "C%04d" % v)
+    bank.finalize()
+    ts = [torch.from_numpy(synth_block(1)).to(dev), torch.from_numpy(synth_block(2)).to(dev)]
+    torch.cuda.synchronize()
+    steps = 20
+    ms, mm, launches = _timed_device_loop(bank, [t.data_ptr() for t in ts], steps, 3)
+    bank.close()
+    del ts
+    gs = 256.0 * BLOCK * steps / (ms * 1e-3) / 1e9
+    out["C"] = {"workload": "256 VFOs x 61.44 MS/s cf32, D=8 + late /5 -> 48 kHz (BASELINE configs[2]); step = one block of %d samples" % BLOCK,
+                "value": gs, "unit": "Gsps", "ms_per_step": ms / steps, "realtime_x": gs * 1e9 / (256 * FS), "launches_per_step": launches,
+                "roofline_frac_fp32": 256.0 * BLOCK * FLOPS_MAIN / (mm * 1e-3) / 1e12 / peak_tflops, "main_kernel_ms": mm,
+                "cpu": cpu_all_core_61m}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -201,9 +390,11 @@ def main():
     ap.add_argument("--vfos", type=int, default=N_VFOS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast", action="store_true", help="skip the tolerance-mode side measurement")
+    ap.add_argument("--no-parity", action="store_true", help="skip the byte-identity leg (never skipped by default)")
+    ap.add_argument("--no-side", action="store_true", help="skip the side lines for BASELINE configs[0..2] and DC correction (N = 1 only)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="N > 1, device-resident value: 'peer' = every GPU's kernel pulls the raw tiles straight out of rank 0's HBM "
-                         "over NVLink (CUDA IPC mapping, fused with the compute); 'nccl' = ncclBroadcast into a local buffer first")
+                    help="N > 1: 'peer' = the raw block lies in N slices, one per GPU, and every GPU's kernel pulls the raw tiles straight out of "
+                         "the owners' HBM over NVLink (CUDA IPC mapping, fused with the compute); 'nccl' = ncclBroadcast from rank 0 into a local buffer first")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
 
@@ -224,50 +415,95 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the DDC bank has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    gloo = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
+        gloo = dist.new_group(backend="gloo")          # host-side barriers that launch nothing on the GPUs
+
+    def host_barrier():
+        if world > 1:
+            dist.barrier(group=gloo)
 
     # ---- bank: this rank's VFO shard (v mod world) ----
     freqs = vfo_freqs(args.vfos)
     from aeroddc.shard import shard_vfos
 
     mine = shard_vfos(args.vfos, world, rank)
-    bank = aeroddc.Bank(FS, BLOCK, aeroddc.CF32, local_rank)
-    for v in mine:
-        bank.add_vfo(float(freqs[v]), DECIM, LATE, 0, GAIN, 1, 1, 1, "V%04d" % v)
+
+    def make_bank(mode=None, dcc=False):
+        b = aeroddc.Bank(FS, BLOCK, aeroddc.CF32, local_rank)
+        for v in mine:
+            b.add_vfo(float(freqs[v]), DECIM, LATE, 0, GAIN, 1, 1, 1, "V%04d" % v)
+        if mode is not None:
+            b.set_mode(mode)
+        if dcc:
+            b.set_dc_correction(True)
+        b.finalize()
+        return b
+
     t0 = time.perf_counter()
-    bank.finalize()
+    bank = make_bank()
     t_finalize = time.perf_counter() - t0
 
-    # ---- inputs: two distinct blocks; pinned on the host (bank ring), and in rank 0's HBM ----
+    # ---- inputs: two distinct blocks in every rank's pinned host ring (a shared-memory ring in a real deployment) ----
     host = [bank.host_slot(0), bank.host_slot(1)]
-    if rank == 0:
-        host[0][:] = synth_block(1)
-        host[1][:] = synth_block(2)
-    dbuf = [torch.empty(2 * BLOCK, dtype=torch.float32, device=dev) for _ in range(2)]   # grown to 4 for N > 1 below
-    src = [torch.empty(2 * BLOCK, dtype=torch.float32, device=dev) for _ in range(2)] if (world > 1 and rank == 0) else None
-    if rank == 0:
-        for i in range(2):
-            (src if world > 1 else dbuf)[i].copy_(torch.from_numpy(host[i]))
-    torch.cuda.synchronize()
+    host[0][:] = synth_block(1)
+    host[1][:] = synth_block(2)
+    peer = world > 1 and args.exchange == "peer"
 
-    # N > 1, --exchange peer: rank 0's two source blocks live in plain cudaMalloc memory exported over CUDA IPC;
-    # every other rank maps them and hands the PEER address to its bank, whose TMA tile loads then read rank 0's
-    # HBM across NVLink while computing (no broadcast step, no staging buffer).
-    peer_ptr = None
-    if world > 1 and args.exchange == "peer":
-        handles = [None, None]
-        own = []
+    # ---- device buffers ----
+    # N = 1 or --exchange nccl: whole blocks in local HBM. peer: this rank holds slice `rank` of every block in plain
+    # cudaMalloc memory exported over CUDA IPC; every rank maps all slices and hands their addresses to its bank, whose
+    # TMA tile loads then read each tile from the GPU that holds it across NVLink while computing.
+    dbuf, src, events = [], None, []
+    slice_len = n_slices = 0
+    res_ptrs = ring_ptrs = ring_events = None
+    RING = 3
+    if peer:
+        slice_len = ((BLOCK + world - 1) // world + 255) // 256 * 256
+        n_slices = (BLOCK + slice_len - 1) // slice_len
+        lo, hi = rank * slice_len, min((rank + 1) * slice_len, BLOCK)
+        my = {"res": [], "ring": []}
+        if rank < n_slices:
+            for i in range(2):
+                ptr = aeroddc.dev_alloc(local_rank, (hi - lo) * 8)
+                aeroddc.dev_upload(local_rank, ptr, host[i][2 * lo:2 * hi])
+                my["res"].append(ptr)
+            for i in range(RING):
+                my["ring"].append(aeroddc.dev_alloc(local_rank, (hi - lo) * 8))
+        my_events = [torch.cuda.Event(enable_timing=False, interprocess=True) for _ in range(RING)]
+        for e in my_events:
+            e.record()
+        torch.cuda.synchronize()
+        pack = {"res": [aeroddc.ipc_export(local_rank, p) for p in my["res"]], "ring": [aeroddc.ipc_export(local_rank, p) for p in my["ring"]],
+                "ev": [e.ipc_handle() for e in my_events]}
+        allp = [None] * world
+        dist.all_gather_object(allp, pack, group=gloo)
+        res_ptrs = [[None] * n_slices for _ in range(2)]
+        ring_ptrs = [[None] * n_slices for _ in range(RING)]
+        ring_events = [[None] * n_slices for _ in range(RING)]
+        keep = []
+        for r in range(n_slices):
+            for i in range(2):
+                res_ptrs[i][r] = my["res"][i] if r == rank else aeroddc.ipc_import(local_rank, allp[r]["res"][i])
+            for i in range(RING):
+                ring_ptrs[i][r] = my["ring"][i] if r == rank else aeroddc.ipc_import(local_rank, allp[r]["ring"][i])
+                ev = my_events[i] if r == rank else torch.cuda.Event.from_ipc_handle(dev, allp[r]["ev"][i])
+                keep.append(ev)
+                ring_events[i][r] = ev.cuda_event
+        copy_stream = torch.cuda.Stream(device=dev)
+    else:
+        nbuf = 4 if world > 1 else 2
+        dbuf = [torch.empty(2 * BLOCK, dtype=torch.float32, device=dev) for _ in range(nbuf)]
+        if world > 1 and rank == 0:
+            src = [torch.empty(2 * BLOCK, dtype=torch.float32, device=dev) for _ in range(2)]
         if rank == 0:
             for i in range(2):
-                ptr = aeroddc.dev_alloc(local_rank, host[i].nbytes)
-                aeroddc.dev_upload(local_rank, ptr, host[i])
-                own.append(ptr)
-                handles[i] = aeroddc.ipc_export(local_rank, ptr)
-        dist.broadcast_object_list(handles, src=0)
-        peer_ptr = own if rank == 0 else [aeroddc.ipc_import(local_rank, h) for h in handles]
+                (src if world > 1 else dbuf)[i].copy_(torch.from_numpy(host[i]))
+        events = [None] * nbuf
+    torch.cuda.synchronize()
 
     def sync_all():
         torch.cuda.synchronize()
@@ -275,35 +511,37 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # N > 1: the raw block travels rank 0 -> all ranks by NCCL broadcast TWO blocks ahead of its use (four device
-    # buffers), so the collective's kernel runs while the previous block's CTAs drain instead of between two blocks.
-    nbuf = 4 if world > 1 else 2
-    while len(dbuf) < nbuf:
-        dbuf.append(torch.empty(2 * BLOCK, dtype=torch.float32, device=dev))
-    events = [None] * nbuf
-
-    def prefetch(k, from_host):
-        """Start moving block k into this rank's HBM buffer k % nbuf (async)."""
-        if world == 1:
+    def upload_my_slice(ring_i, block_np, blocking=False):
+        """H2D of this rank's slice of a host block into its ring buffer; records the slice's interprocess event."""
+        if rank >= n_slices:
             return
-        b = k % nbuf
+        lo, hi = rank * slice_len, min((rank + 1) * slice_len, BLOCK)
+        if blocking:
+            aeroddc.dev_upload(local_rank, ring_ptrs[ring_i][rank], block_np[2 * lo:2 * hi])
+            return
+        with torch.cuda.stream(copy_stream):
+            aeroddc.dev_upload_async(local_rank, ring_ptrs[ring_i][rank], block_np[2 * lo:2 * hi], copy_stream.cuda_stream)
+            my_events[ring_i].record(copy_stream)
+
+    def prefetch_nccl(k, from_host, b=None):
+        """--exchange nccl: start moving block k into this rank's HBM buffer k % nbuf (async): H2D or D2D on rank 0, then broadcast."""
+        i = k % len(dbuf)
         if rank == 0:
             if from_host:
-                dbuf[b].copy_(torch.from_numpy(host[k & 1]), non_blocking=True)    # H2D from the pinned ring
+                dbuf[i].copy_(torch.from_numpy(host[k & 1]), non_blocking=True)    # H2D from the pinned ring
             else:
-                dbuf[b].copy_(src[k & 1], non_blocking=True)                        # stays in HBM
-        dist.broadcast(dbuf[b], src=0)
+                dbuf[i].copy_(src[k & 1], non_blocking=True)                        # stays in HBM
+        dist.broadcast(dbuf[i], src=0)
         e = torch.cuda.Event()
         e.record()
-        events[b] = e
+        events[i] = e
 
-    def run_blocks(n, from_host, on_wait=None, allow_peer=True):
-        """n blocks, two in flight. from_host: the host-facing path (pinned host blocks, H2D inside)."""
-        peer = peer_ptr is not None and not from_host and allow_peer
-        for k in range(min(2, n)):
-            if not peer:
-                prefetch(k, from_host)
+    def run_blocks(bank, n, from_host, on_wait=None):
+        """n blocks, two in flight. from_host: the host-facing path (pinned host blocks, H2D of every block inside)."""
         inflight = 0
+        if world > 1 and not peer:
+            for k in range(min(2, n)):
+                prefetch_nccl(k, from_host)
         for k in range(n):
             if inflight == 2:
                 bank.wait(); inflight -= 1
@@ -315,28 +553,30 @@ def main():
                 else:
                     bank.submit_device(dbuf[k & 1].data_ptr(), None)
             elif peer:
-                bank.submit_device(peer_ptr[k & 1], None)      # the kernel reads rank 0's HBM directly
+                if from_host:
+                    # every rank uploads its own 1/N of the block over its own PCIe link; the ring is three deep, so the
+                    # buffers of block k-3 are free (all ranks passed the barrier of block k-1, i.e. retired block k-3)
+                    r = k % RING
+                    upload_my_slice(r, host[k & 1])
+                    host_barrier()                       # every rank has recorded its slice event of this round
+                    bank.submit_device_sliced(ring_ptrs[r], slice_len, ring_events[r])
+                else:
+                    bank.submit_device_sliced(res_ptrs[k & 1], slice_len)
             else:
-                b = k % nbuf
-                bank.submit_device(dbuf[b].data_ptr(), events[b].cuda_event)
+                i = k % len(dbuf)
+                bank.submit_device(dbuf[i].data_ptr(), events[i].cuda_event)
                 if k + 2 < n:
-                    prefetch(k + 2, from_host)       # buffer (k+2) % 4 was last read by block k-2, which has completed
+                    prefetch_nccl(k + 2, from_host)      # buffer (k+2) % 4 was last read by block k-2, which has completed
             inflight += 1
         while inflight:
             bank.wait(); inflight -= 1
             if on_wait:
                 on_wait()
 
-    def run_device(n):
-        run_blocks(n, False)
-
-    def run_e2e(n):
-        run_blocks(n, True)
-
     peak_tflops, probe_clock = aeroddc.measure_fp32_peak(local_rank)
 
     # ---- timed region 1: inputs resident in HBM ----
-    run_device(args.warmup)
+    run_blocks(bank, args.warmup, False)
     sync_all()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -344,41 +584,80 @@ def main():
     main_ms = []
     bank.stopwatch_start(False)
     t0 = time.perf_counter()
-    run_blocks(args.steps, False, on_wait=lambda: main_ms.append(bank.last_main_ms()))
+    run_blocks(bank, args.steps, False, on_wait=lambda: main_ms.append(bank.last_main_ms()))
     dev_ms = bank.stopwatch_stop()
     sync_all()
     wall_ms = (time.perf_counter() - t0) * 1e3
     kern_ms, launches_per_step = bank.last_timing()
 
     # ---- timed region 2: end to end through the host-facing API ----
-    run_e2e(2)
+    run_blocks(bank, 3, True)
     sync_all()
     t0 = time.perf_counter()
-    run_e2e(args.steps)
+    run_blocks(bank, args.steps, True)
     sync_all()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- parity: the same bank, rewound, six distinct blocks through the same device path, against the reference chain ----
+    parity = None
+    if not args.no_parity:
+        n = len(mine)
+        picks = sorted(set([0, n - 1] + [int(round(i * (n - 1) / 7.0)) for i in range(1, 7)]))
+        bank.reset()
+        pblocks = [parity_block(k) for k in range(PARITY_BLOCKS)]
+        got = [[] for _ in picks]
+        for k, x in enumerate(pblocks):
+            if world == 1:
+                dbuf[k & 1].copy_(torch.from_numpy(x))
+                torch.cuda.synchronize()
+                bank.submit_device(dbuf[k & 1].data_ptr(), None)
+            elif peer:
+                upload_my_slice(k % RING, x, blocking=True)
+                host_barrier()
+                bank.submit_device_sliced(ring_ptrs[k % RING], slice_len)
+            else:
+                if rank == 0:
+                    dbuf[k & 1].copy_(torch.from_numpy(x))
+                dist.broadcast(dbuf[k & 1], src=0)
+                torch.cuda.synchronize()
+                bank.submit_device(dbuf[k & 1].data_ptr(), None)
+            bank.wait()
+            host_barrier()
+            for j, i in enumerate(picks):
+                got[j].append(bank.output(i)[0])
+        kind, bad = parity_check(pblocks, [(DECIM, LATE, float(freqs[mine[i]]), GAIN) for i in picks], got)
+        nz = sum(1 for g in got for p in g if any(p))
+        parity = {"vfos": len(picks), "blocks": PARITY_BLOCKS, "byte_identical": not bad, "mismatches": len(bad),
+                  "nonzero_payloads": nz, "against": "oracle/_ref (unmodified reference vfo.cpp chain)" if kind == "reference" else "oracle port (ddc_oracle.c)",
+                  "exchange": "peer" if peer else ("nccl" if world > 1 else "local"),
+                  "vfo_ids": [int(mine[i]) for i in picks]}
+        del pblocks
+
     # ---- tolerance mode (AERODDC_MODE_FAST), reported beside the byte-identical headline ----
     fast_ms = None
+    fast_main = []
     if not args.no_fast:
-        fbank = aeroddc.Bank(FS, BLOCK, aeroddc.CF32, local_rank)
-        for v in mine:
-            fbank.add_vfo(float(freqs[v]), DECIM, LATE, 0, GAIN, 1, 1, 1, "V%04d" % v)
-        fbank.set_mode(aeroddc.MODE_FAST)
-        fbank.finalize()
-        main_bank, bank = bank, fbank
-        run_blocks(args.warmup, False, allow_peer=False)
+        fbank = make_bank(mode=aeroddc.MODE_FAST)
+        run_blocks(fbank, args.warmup, False)
         sync_all()
-        fast_main = []
-        bank.stopwatch_start(False)
-        # the tolerance mode consumes raw samples ~1.6x faster; at 8 GPUs seven peers pulling from rank 0 would saturate its
-        # NVLink egress, so this side measurement distributes the block with the NCCL broadcast instead
-        run_blocks(args.steps, False, on_wait=lambda: fast_main.append(bank.last_main_ms()), allow_peer=False)
-        fast_ms = bank.stopwatch_stop()
+        fbank.stopwatch_start(False)
+        run_blocks(fbank, args.steps, False, on_wait=lambda: fast_main.append(fbank.last_main_ms()))
+        fast_ms = fbank.stopwatch_stop()
         sync_all()
         fbank.close()
-        bank = main_bank
+
+    # ---- DC correction on (publisher.cpp:292-296): the sequential recurrence runs one block ahead on its own stream ----
+    dcc_ms = None
+    if not args.no_side and world == 1:
+        dbank = make_bank(dcc=True)
+        ds = 6
+        run_blocks(dbank, 3, False)
+        torch.cuda.synchronize()
+        dbank.stopwatch_start(False)
+        run_blocks(dbank, ds, False)
+        dcc_ms = dbank.stopwatch_stop() / ds
+        dbank.close()
 
     if world > 1:
         t = torch.tensor([dev_ms, e2e_ms, wall_ms, fast_ms or 0.0], dtype=torch.float64, device=dev)
@@ -388,7 +667,14 @@ def main():
         n_mine = torch.tensor([len(mine)], dtype=torch.int64, device=dev)
         dist.all_reduce(n_mine)
         assert int(n_mine.item()) == args.vfos
+        if parity is not None:
+            allp = [None] * world
+            dist.all_gather_object(allp, parity, group=gloo)
+            parity = {"vfos": sum(p["vfos"] for p in allp), "blocks": PARITY_BLOCKS, "byte_identical": all(p["byte_identical"] for p in allp),
+                      "mismatches": sum(p["mismatches"] for p in allp), "nonzero_payloads": sum(p["nonzero_payloads"] for p in allp),
+                      "against": allp[0]["against"], "exchange": allp[0]["exchange"], "per_rank_vfo_ids": [p["vfo_ids"] for p in allp]}
 
+    rc = 0
     if rank == 0:
         total = float(args.vfos) * BLOCK * args.steps
         value = total / (dev_ms * 1e-3) / 1e9
@@ -407,7 +693,14 @@ def main():
         mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(mp):
             hbm_peak = json.load(open(mp)).get("hbm_gbs")
-        alg_bytes = BLOCK * 8.0 + len(mine) * (BLOCK >> DECIM) * 8.0   # raw block read once + stage-D stream written
+        alg_bytes = BLOCK * 8.0 + len(mine) * (BLOCK >> 5) * 8.0   # raw block read once + stage-5 stream written
+        if world == 1:
+            par_text = "single GPU"
+        elif peer:
+            par_text = ("vfo-shard x%d; the raw block lies in %d slices, one per GPU (each GPU ingests its slice over its own PCIe link in the e2e leg), "
+                        "and every GPU's kernel reads all slices in place over NVLink (peer memory, TMA tile loads); no collective on the data path" % (world, n_slices))
+        else:
+            par_text = "vfo-shard x%d, NCCL broadcast of the raw block from rank 0" % world
         line = {
             "metric": "aggregate VFO-channel input samples/s", "value": value, "unit": "Gsps",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -417,14 +710,14 @@ def main():
                             % (args.vfos, len(mine), BLOCK),
                 "n_vfos": args.vfos, "block_len": BLOCK, "sample_rate": FS,
                 "l2": "two alternating 123 MB raw blocks (246 MB > 126 MB L2); no explicit flush",
-                "parallelism": ("vfo-shard x%d, raw block read from rank 0's HBM over NVLink inside the kernel (peer memory); e2e leg: NCCL broadcast" % world if args.exchange == "peer" else "vfo-shard x%d, NCCL broadcast of the raw block" % world) if world > 1 else "single GPU",
+                "parallelism": par_text,
                 "realtime_x": value * 1e9 / (args.vfos * FS),
                 "finalize_s": t_finalize, "device_mb": bank.device_bytes() / 1e6,
                 "flop_per_vfo_sample": FLOPS_TOTAL,
             },
             "e2e": {"value": e2e, "unit": "Gsps", "h2d_bytes_per_step": BLOCK * 8,
                     "d2h_bytes_per_step": int(args.vfos * (BLOCK >> DECIM) // LATE * 2),
-                    "note": "aeroddc_bank_submit/wait with pinned host blocks, two blocks in flight; wall clock between device syncs"},
+                    "note": "pinned host blocks, two blocks in flight, H2D of every block (N > 1: 1/N per GPU, concurrently) and D2H of every payload inside; wall clock between device syncs"},
             "gpu_launches": int(launches_per_step * args.steps * (2 if fast_ms is None else 3)),
             "roofline": {
                 "bound": "fp32", "kernel": "ddc_main_kernel", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
@@ -432,25 +725,39 @@ def main():
                 "peak_source": "FFMA2 issue probe measured in this run (aeroddc_measure_fp32_peak, FMA = 2 flop); MEASURED_PEAKS.json carries no FP32 figure",
                 "launch_ms": mm, "share_of_step": mm / (dev_ms / args.steps),
                 "algorithmic_flop_per_vfo_sample": FLOPS_MAIN,
-                "issue_bound_note": "the reference's arithmetic is un-fused (1 flop per lane-op) plus a 14 lane-op exact NCO step, so 100%% FP32-pipe use = %.1f%% of the FMA peak" % (100 * FLOPS_MAIN / (2 * (FLOPS_MAIN + 14.0))),
+                "issue_bound_note": "the reference's arithmetic is un-fused (1 flop per lane-op; only the half-band centre tap 0.5 fuses exactly) plus a 14 lane-op exact NCO step: "
+                                    "100%% FP32-pipe use = %.1f%% of the FMA peak" % (100 * FLOPS_MAIN / (2 * 37.4)),
                 "hbm": {"achieved_gbs": alg_bytes / (mm * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                         "frac": (alg_bytes / (mm * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None},
             },
+            "parity": parity,
             "clocks": clocks,
             "fast_mode": None if fast_ms is None else {
                 "value": total / (fast_ms * 1e-3) / 1e9, "unit": "Gsps", "ms_per_step": fast_ms / args.steps,
                 "roofline_frac": float(len(mine)) * BLOCK * FLOPS_MAIN / (float(np.mean(fast_main)) * 1e-3) / 1e12 / peak_tflops,
                 "note": "AERODDC_MODE_FAST: fused multiply-adds + rotation-only oscillator between exact checkpoints; NOT bit-identical, "
-                        "within max|err| <= 1e-4 FS / SNR >= 80 dB (tests/test_gpu_parity.py::test_fast_mode_within_stated_tolerance); "
-                        "the headline value above is the byte-identical mode"},
+                        "within max|err| <= 1e-4 FS / SNR >= 80 dB (tests/test_gpu_parity.py::test_fast_mode_within_stated_tolerance, decoded frames identical: "
+                        "tests/test_e2e_decode.py); the headline value above is the byte-identical mode"},
             "wall_ms_per_step": wall_ms / args.steps,
         }
+        if dcc_ms is not None:
+            line["dc_correction"] = {"value": float(args.vfos) * BLOCK / (dcc_ms * 1e-3) / 1e9, "unit": "Gsps", "ms_per_step": dcc_ms,
+                                     "realtime_x": 250.0 / dcc_ms,
+                                     "note": "--enable-dcc: the exact sequential DC-removal recurrence (one thread per rail) runs on its own stream one block ahead of the VFO kernels"}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(np.array(host[0]))
+        if not args.no_side and world == 1:
+            cb = line.get("cpu_baseline")
+            line["configs"] = side_configs(aeroddc, torch, dev, local_rank, peak_tflops,
+                                           None if cb is None else {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")})
         print(json.dumps(line))
+        if parity is not None and not parity["byte_identical"]:
+            sys.stderr.write("bench.py: PARITY FAILURE: %d payloads differ from the reference chain\n" % parity["mismatches"])
+            rc = 1
     bank.close()
     if world > 1:
         dist.destroy_process_group()
+    sys.exit(rc)
 
 
 if __name__ == "__main__":

@@ -211,7 +211,10 @@ def test_publisher_over_zeromq_into_the_decoder(tmp_path):
         sub.setsockopt(zmq.SUBSCRIBE, topic.encode())
     sub.setsockopt(zmq.RCVHWM, 100000)
     sub.setsockopt(zmq.RCVTIMEO, 500)
-    proc = subprocess.Popen([BIN, "-d", "file=%s,format=cu8,delay=2,throttle=8" % iq, str(ini)], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    import glob
+    libs = glob.glob(os.path.join(os.path.dirname(zmq.__file__), "..", "pyzmq.libs", "libzmq*.so*"))   # pyzmq's bundled libzmq
+    env = dict(os.environ, AERODDC_LIBZMQ=os.path.abspath(libs[0])) if libs else dict(os.environ)
+    proc = subprocess.Popen([BIN, "-d", "file=%s,format=cu8,delay=2,throttle=8" % iq, str(ini)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
     got = {}
     try:
         sub.connect("tcp://127.0.0.1:%d" % port)

@@ -155,9 +155,8 @@ def test_reference_publisher_on_the_product_vfo_class_has_no_cpu_path(tmp_path):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(GPUVFO), reason="oracle/_ref/ref_publish_gpuvfo not built (make -C oracle refpublish_gpuvfo)")
-@pytest.mark.xfail(not os.environ.get("AERODDC_RUN_UNVERIFIED"), strict=False,
-                   reason="built after round 1's GPU minutes were spent: its first hardware run is the round-end suite; XPASS = it works")
-@pytest.mark.parametrize("name,fmt,dcc", [("e2e_288k.ini", "cu8", True), ("two_mains_1920k.ini", "cf32", False)])
+@pytest.mark.parametrize("name,fmt,dcc", [("e2e_288k.ini", "cu8", True), ("two_mains_1920k.ini", "cf32", False), ("two_mains_1920k.ini", "cu8", True),
+                                          ("sdr_54W_style_1536k.ini", "cs16", False)])
 def test_reference_publisher_source_drives_the_product_vfo_class(tmp_path, name, fmt, dcc):
     """Drop-in at link level: the reference's own Publisher (settings, reader loop, DC correction - all its code) calls
     setFs / setDecimationCount / ... / init / process on the product's vfo objects, one private GPU bank per main VFO.
