@@ -90,11 +90,11 @@ __device__ __forceinline__ unsigned long long tl_pack(float a, float b) { unsign
 __device__ __forceinline__ unsigned long long tl_mul(unsigned long long a, unsigned long long b) { unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ unsigned long long tl_fma(unsigned long long a, unsigned long long b, unsigned long long c) { unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 
-__global__ void __launch_bounds__(kTailThreads) tail_kernel(const TailVfo* __restrict__ vfos, float one, size_t out_offset) {
-  extern __shared__ __align__(16) unsigned char tsm[];
-  TailVfo v = vfos[blockIdx.y];
+// one (VFO, chunk of kTailChunk outputs) item; every thread of the CTA takes the same path through it
+__device__ __forceinline__ void tail_item(const TailVfo* __restrict__ vfos, int vfo_i, int chunk, float one, size_t out_offset, unsigned char* tsm) {
+  TailVfo v = vfos[vfo_i];
   v.out += out_offset;   // payload rows are double-buffered by block parity
-  const int k0 = blockIdx.x * kTailChunk;
+  const int k0 = chunk * kTailChunk;
   if (k0 >= v.n_out) return;
   const int kc = min(kTailChunk, v.n_out - k0);
   const int tid = threadIdx.x;
@@ -186,6 +186,24 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(const TailVfo* __res
       y = u[k];
     }
     o16[k0 + k] = to_short_x86(__fmul_rn(y, v.gain));
+  }
+}
+
+// Persistent grid: CTAs take (VFO, chunk) items from a counter (zeroed by the host before every launch). The bank
+// launches about one CTA per SM on its high-priority post-processing stream, so the tail of block k runs in a few SM
+// slots beside the main kernel of block k+1 instead of displacing it.
+__global__ void __launch_bounds__(kTailThreads) tail_kernel(const TailVfo* __restrict__ vfos, float one, size_t out_offset,
+                                                             int* counter, int n_vfos, int chunks_per_vfo) {
+  extern __shared__ __align__(16) unsigned char tsm[];
+  __shared__ int s_item;
+  const int n_items = n_vfos * chunks_per_vfo;
+  for (;;) {
+    if (threadIdx.x == 0) s_item = atomicAdd(counter, 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= n_items) break;
+    tail_item(vfos, item / chunks_per_vfo, item % chunks_per_vfo, one, out_offset, tsm);
+    __syncthreads();   // shared memory and s_item are reused by the next item
   }
 }
 

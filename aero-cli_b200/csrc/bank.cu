@@ -73,11 +73,13 @@ struct Group {   // VFOs sharing input stream and DA = min(D, 5): one launch of 
   int DA, Dmax, base, count;
   int fs_in, blk_in;
   int S, W, Wb, nseg;
-  int Q, P;          // parts per segment and part length (chained CTAs, see ddc_kernels.cuh)
+  int Q, P;          // parts per full segment and part length (chained CTAs, see ddc_kernels.cuh)
+  int nchains, nparts; // chains = 32-VFO groups x segments; parts of all chains together (the last segment may be shorter)
   int mid_pitch;     // VFO pitch of the stage-DA stream: count rounded up to a warp
   int n_mid;         // stage-DA samples per block
   int deep_T, deep_ranges;
-  int* d_flags = nullptr;
+  int* d_sched = nullptr;      // [2 + nchains + (nparts - nchains)] scheduler words of the main kernel
+  size_t sched_words = 0;
   float2* d_hand = nullptr;
   float2* d_mid[2] = {nullptr, nullptr};   // [n_mid][mid_pitch], by block parity
 };
@@ -113,6 +115,7 @@ struct aeroddc_bank {
   bool dcc = false;
   float* d_dcc_out[2] = {nullptr, nullptr};   // DC-corrected cf32 block, by block parity (block k+1 is corrected while block k computes)
   float* d_dcc_state = nullptr;  // running average per rail
+  size_t dcc_smem = 0;           // dynamic shared memory the DC kernel asks for (a whole SM's worth, see enqueue_block)
   bool nested = false;           // some VFO feeds sub-VFOs: the groups then run strictly in order on one stream
   bool poisoned = false;         // a chained CTA gave up waiting: every later call fails
   std::vector<VfoRec> vfos;
@@ -129,6 +132,8 @@ struct aeroddc_bank {
   float2* d_xd = nullptr;       // all stage-D rows, per VFO: [hist][n_stage]
   float2** d_xd_rows = nullptr; // [vfo_pitch] pointer to stage-D index 0 of each column's row
   int* d_nco_len = nullptr;     // [vfo_pitch]
+  int* d_post_ctr = nullptr;    // work-item counters of the persistent post-processing kernels: [0] tail, [1 + g] deep kernel of group g
+  int post_ctas_deep = 0, post_ctas_tail = 0;   // their grid sizes
   int* d_err = nullptr;         // chained-CTA watchdog flag: device view of h_err (zero-copy pinned host memory)
   volatile int* h_err = nullptr;
   int nck_max = 0;
@@ -199,9 +204,10 @@ cudaError_t launch_main(int fmt, int nf, const MainParams& p, dim3 grid, cudaStr
 void free_all(aeroddc_bank* b) {
   cudaSetDevice(b->device);
   cudaDeviceSynchronize();
+  cudaFree(b->d_post_ctr);
   cudaFree(b->d_rot); cudaFree(b->d_qlast); cudaFree(b->d_ckpt); cudaFree(b->d_vfo_D);
   for (int i = 0; i < 3; ++i) cudaFree(b->d_state[i]);
-  for (Group& g : b->groups) { cudaFree(g.d_flags); cudaFree(g.d_hand); cudaFree(g.d_mid[0]); cudaFree(g.d_mid[1]); }
+  for (Group& g : b->groups) { cudaFree(g.d_sched); cudaFree(g.d_hand); cudaFree(g.d_mid[0]); cudaFree(g.d_mid[1]); }
   if (b->h_err) cudaFreeHost((void*)b->h_err);
   cudaFree(b->d_dcc_out[0]); cudaFree(b->d_dcc_out[1]); cudaFree(b->d_dcc_state);
   cudaFree(b->d_xd); cudaFree(b->d_xd_rows); cudaFree(b->d_nco_len); cudaFree(b->d_taps); cudaFree(b->d_hil_idx); cudaFree(b->d_tail); cudaFree(b->d_out);
@@ -235,10 +241,15 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
   int launches = 0;
   RawBlock raw = raw_in;
   int raw_fmt = b->fmt;
-  if (b->dcc) {   // sequential DC removal of the raw stream, one block ahead of the VFOs, which then read the corrected cf32 block
-    if (b->fmt == AERODDC_CU8) dcc_kernel<0><<<1, 32, 0, b->s_dcc>>>(raw, b->d_dcc_out[par], b->d_dcc_state, b->B);
-    else if (b->fmt == AERODDC_CS16) dcc_kernel<1><<<1, 32, 0, b->s_dcc>>>(raw, b->d_dcc_out[par], b->d_dcc_state, b->B);
-    else dcc_kernel<2><<<1, 32, 0, b->s_dcc>>>(raw, b->d_dcc_out[par], b->d_dcc_state, b->B);
+  if (b->dcc) {
+    // Sequential DC removal of the raw stream, one block ahead of the VFOs, which then read the corrected cf32 block.
+    // The recurrence is one dependent FMUL + FADD per sample; next to 16 warps that saturate the FP32 pipe its single
+    // warp would be starved (measured: 19x slower), so the CTA asks for a whole SM's shared memory and thereby keeps
+    // the SM to itself: 1/148 of the machine for the rate-limiting step of a DC-corrected stream.
+    const size_t ex = b->dcc_smem;
+    if (b->fmt == AERODDC_CU8) dcc_kernel<0><<<1, 32, ex, b->s_dcc>>>(raw, b->d_dcc_out[par], b->d_dcc_state, b->B);
+    else if (b->fmt == AERODDC_CS16) dcc_kernel<1><<<1, 32, ex, b->s_dcc>>>(raw, b->d_dcc_out[par], b->d_dcc_state, b->B);
+    else dcc_kernel<2><<<1, 32, ex, b->s_dcc>>>(raw, b->d_dcc_out[par], b->d_dcc_state, b->B);
     CU(cudaGetLastError());
     ++launches;
     CU(cudaEventRecord(b->ev_dcc[par], b->s_dcc));
@@ -249,6 +260,7 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
     raw_fmt = AERODDC_CF32;
   }
   CU(cudaEventRecord(b->ev_k0[slot], sA));
+  if (b->nested) CU(cudaMemsetAsync(b->d_post_ctr, 0, sizeof(int) * (1 + b->groups.size()), sA));
   CU(cudaEventRecord(b->ev_m0[slot], sA));
   const float2* state_in = b->d_state[k % 3];
   float2* state_out = b->d_state[(k + 1) % 3];
@@ -259,6 +271,7 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
     d.state_in = state_in;
     d.xd_rows = b->d_xd_rows;
     d.vfo_D = b->d_vfo_D;
+    d.counter = b->d_post_ctr + 1 + (&g - &b->groups[0]);
     d.vfo_pitch = b->vfo_pitch;
     d.mid_pitch = g.mid_pitch;
     d.vfo_base = g.base;
@@ -268,10 +281,12 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
     d.T = g.deep_T;
     d.Wd = kDeepWarm;
     d.nranges = g.deep_ranges;
+    d.ngroups = (g.count + 31) / 32;
     d.one = 1.0f;
-    dim3 grid((unsigned)((g.count + 31) / 32), (unsigned)((g.deep_ranges + kDeepWarps - 1) / kDeepWarps));
-    if (fast) ddc_deep_kernel<true><<<grid, 32 * kDeepWarps, 0, st>>>(d);
-    else ddc_deep_kernel<false><<<grid, 32 * kDeepWarps, 0, st>>>(d);
+    const int items = d.nranges * d.ngroups;
+    const unsigned grid = (unsigned)std::min(items, b->post_ctas_deep);
+    if (fast) ddc_deep_kernel<true><<<grid, 32, 0, st>>>(d);
+    else ddc_deep_kernel<false><<<grid, 32, 0, st>>>(d);
     CU(cudaGetLastError());
     ++launches;
     return AERODDC_OK;
@@ -308,15 +323,14 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
     p.one = 1.0f;
     p.transient = 4 * kNcoStride;
     p.nck = b->nck_max;
-    p.Q = g.Q;
     p.P = g.P;
     p.ngroups = (g.count + kVfoPerCta - 1) / kVfoPerCta;
-    p.flags = g.d_flags;
-    p.ticket = g.d_flags + (size_t)p.ngroups * g.nseg;   // the counter lives behind the flags
+    p.nchains = g.nchains;
+    p.sched = g.d_sched;
     p.hand = g.d_hand;
     p.err = b->d_err;
-    CU(cudaMemsetAsync(g.d_flags, 0, sizeof(int) * ((size_t)p.ngroups * g.nseg + 1), sA));
-    dim3 grid((unsigned)(p.ngroups * (1 + g.Q * g.nseg)));
+    CU(cudaMemsetAsync(g.d_sched, 0, sizeof(int) * g.sched_words, sA));
+    dim3 grid((unsigned)(p.ngroups + g.nparts));
     CU(launch_main(g.parent < 0 ? raw_fmt : AERODDC_CF32, g.DA, p, grid, sA, fast));
     ++launches;
     if (b->nested) { const int rc = launch_deep(g, sA); if (rc != AERODDC_OK) return rc; }
@@ -325,13 +339,15 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
   if (!b->nested) {
     CU(cudaEventRecord(b->ev_main[par], sA));
     CU(cudaStreamWaitEvent(sB, b->ev_main[par], 0));
+    CU(cudaMemsetAsync(b->d_post_ctr, 0, sizeof(int) * (1 + b->groups.size()), sB));
     for (const Group& g : b->groups) { const int rc = launch_deep(g, sB); if (rc != AERODDC_OK) return rc; }
   }
   {
     // payload rows are double-buffered by block parity; wait until the copy-out of this parity (two blocks ago) is done
     if (k >= 2) CU(cudaStreamWaitEvent(sB, b->ev_d2h[par], 0));
-    dim3 grid(b->tail_chunks, (unsigned)b->vfos.size());
-    tail_kernel<<<grid, kTailThreads, b->tail_smem, sB>>>(b->d_tail, 1.0f, (size_t)par * b->out_total);
+    const int items = b->tail_chunks * (int)b->vfos.size();
+    tail_kernel<<<(unsigned)std::min(items, b->post_ctas_tail), kTailThreads, b->tail_smem, sB>>>(
+        b->d_tail, 1.0f, (size_t)par * b->out_total, b->d_post_ctr, (int)b->vfos.size(), b->tail_chunks);
     CU(cudaGetLastError());
     ++launches;
   }
@@ -420,11 +436,12 @@ int aeroddc_plan_segments(int block_len, int decim_count, int n_vfos, int n_sm, 
   out->warmup = DA == 0 ? 0 : ((10 << DA) + cstep - 1) / cstep * cstep;     // 10*(2^DA - 1) samples reach the last register stage's history
   out->boundary_warmup = decim_count == 0 ? 0 : (11 << decim_count);        // the next block's shifted history needs 11 samples per stage
   const int groups = (n_vfos + kVfoPerCta - 1) / kVfoPerCta;
-  // One wave of one-warp CTAs (kCtasPerSm per SM) cuts the block into segments, each paying one warm-up of W samples.
-  // The warp scheduler favours some resident warps, so equal CTAs of a single wave finish at different times;
-  // each segment is therefore processed as Q chained parts by Q short CTAs (state handed over through HBM),
-  // which evens the load without further warm-ups.
-  const int target = std::max(1, (int)std::floor((double)kCtasPerSm * n_sm * waves / groups) - 1);   // -1: the boundary CTA
+  // One wave of one-warp CTAs (kCtasPerSm per SM), plus a few percent, cuts the block into segments, each paying one
+  // warm-up of W samples. The warp scheduler favours some resident warps, so equal CTAs of a single wave would finish
+  // at different times; each segment is therefore a chain of Q parts handed from CTA to CTA through HBM, and the
+  // kernel's FIFO of ready chains (a few more chains than SM slots keep it non-empty) lets every chain advance at the
+  // average pace of all slots.
+  const int target = std::max(1, (int)std::ceil((double)kCtasPerSm * n_sm * waves * 1.04 / groups));
   int S = (block_len + target - 1) / target;
   S = std::max(S, std::max(4 * out->warmup, 2048));
   S = (S + align - 1) / align * align;
@@ -437,7 +454,9 @@ int aeroddc_plan_segments(int block_len, int decim_count, int n_vfos, int n_sm, 
   out->parts = Q;
   out->part_len = ((S + Q - 1) / Q + pal - 1) / pal * pal;
   out->vfo_groups = groups;
-  out->ctas = groups * (1 + Q * out->n_segments);
+  const int last = block_len - (out->n_segments - 1) * S;                      // the last segment may be shorter
+  const int parts_total = (out->n_segments - 1) * ((S + out->part_len - 1) / out->part_len) + (last + out->part_len - 1) / out->part_len;
+  out->ctas = groups * (1 + parts_total);
   return AERODDC_OK;
 }
 
@@ -543,12 +562,25 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
     g.n_mid = g.blk_in >> g.DA;
     g.deep_T = g.n_mid >= 65536 ? 1024 : 256;
     g.deep_ranges = (g.n_mid + g.deep_T - 1) / g.deep_T;
-    const size_t nk = (size_t)((g.count + kVfoPerCta - 1) / kVfoPerCta) * g.nseg;
-    CU(dmalloc((void**)&g.d_flags, sizeof(int) * (nk + 1)));   // + the ticket counter
-    CU(cudaMemset(g.d_flags, 0, sizeof(int) * (nk + 1)));
-    CU(dmalloc((void**)&g.d_hand, sizeof(float2) * nk * kHandSlots * kThreads));
+    const int ng = (g.count + kVfoPerCta - 1) / kVfoPerCta;
+    g.nchains = ng * g.nseg;
+    g.nparts = pl.ctas - ng;
+    g.sched_words = 2 + (size_t)g.nparts;   // counters + parts done per chain + queue (one entry per part after a chain's first)
+    CU(dmalloc((void**)&g.d_sched, sizeof(int) * g.sched_words));
+    CU(cudaMemset(g.d_sched, 0, sizeof(int) * g.sched_words));
+    CU(dmalloc((void**)&g.d_hand, sizeof(float2) * (size_t)g.nchains * kHandSlots * kThreads));
     for (int i = 0; i < 2; ++i) CU(dmalloc((void**)&g.d_mid[i], sizeof(float2) * (size_t)g.n_mid * g.mid_pitch));
   }
+  CU(dmalloc((void**)&b->d_post_ctr, sizeof(int) * (1 + b->groups.size())));
+  // Persistent grids of the post-processing kernels, in CTAs per SM. A flat bank overlaps block k's post-processing with
+  // block k+1's main kernel; measured on B200, a few light warps per SM beside the FP32-saturating main kernel are starved
+  // by the warp scheduler (2 + 1 CTAs per SM: the deep kernel then takes longer than the main kernel, 25 ms per step instead
+  // of 21), so both kernels take whole SMs' worth of slots for a short time instead.
+  const char* env_post = getenv("AERODDC_POST_CTAS");   // experiments: "deep,tail" CTAs per SM
+  int per_sm_deep = 16, per_sm_tail = 6;
+  if (env_post) sscanf(env_post, "%d,%d", &per_sm_deep, &per_sm_tail);
+  b->post_ctas_deep = std::max(1, per_sm_deep) * b->n_sm;
+  b->post_ctas_tail = std::max(1, per_sm_tail) * b->n_sm;
   CU(cudaHostAlloc((void**)&b->h_err, sizeof(int), cudaHostAllocMapped));
   *b->h_err = 0;
   CU(cudaHostGetDevicePointer((void**)&b->d_err, (void*)b->h_err, 0));
@@ -657,6 +689,10 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
   CU(cudaMemcpy(b->d_tail, h_tail.data(), sizeof(TailVfo) * nv, cudaMemcpyHostToDevice));
 
   if (b->dcc) {
+    b->dcc_smem = (size_t)prop.sharedMemPerBlockOptin;   // everything an SM can give one CTA: no other CTA fits beside it
+    CU(cudaFuncSetAttribute(dcc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->dcc_smem));
+    CU(cudaFuncSetAttribute(dcc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->dcc_smem));
+    CU(cudaFuncSetAttribute(dcc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->dcc_smem));
     for (int i = 0; i < 2; ++i) CU(dmalloc((void**)&b->d_dcc_out[i], sizeof(float) * 2 * (size_t)b->B));
     CU(dmalloc((void**)&b->d_dcc_state, sizeof(float) * 2));
     CU(cudaMemset(b->d_dcc_state, 0, sizeof(float) * 2));

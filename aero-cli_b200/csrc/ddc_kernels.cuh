@@ -61,6 +61,9 @@ __device__ __forceinline__ P2 fma2(P2 a, P2 b, P2 c) { P2 d; asm("fma.rn.f32x2 %
 // FFMA2, FMUL2 and FADD2 share one pipe and one rate.
 struct Ones { P2 one; };
 __device__ __forceinline__ P2 add2(const Ones& k, P2 a, P2 b) { return fma2(a, k.one, b); }
+// A true FADD2, for sums whose operands are never products (the tap-pair sums of the half-band filter): there is no
+// multiply ptxas could fuse it with, and it reads two register pairs instead of three operands.
+__device__ __forceinline__ P2 addp(P2 a, P2 b) { P2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v)); return d; }
 __device__ __forceinline__ P2 mul2s(P2 a, float s) { return mul2(a, bcast2(s)); }   // FMUL2 R, R.F32x2, R.F32
 __device__ __forceinline__ P2 pzero() { P2 z; z.v = 0ull; return z; }
 
@@ -102,7 +105,7 @@ struct HbState { P2 e[5]; P2 o[3]; };
 // values end as 0 in every int16 / int8 payload either way (tests/test_gpu_parity.py::test_subnormal_inputs_...).
 // -DAERODDC_HB_CENTER_MUL restores the separate multiply (one more FMUL2 per half-band output).
 __device__ __forceinline__ P2 hb_out(const Ones& k, P2 e0, P2 e1, P2 e2, P2 e3, P2 e4, P2 xe, P2 o0) {
-  P2 s0 = add2(k, e0, xe), s2 = add2(k, e1, e4), s4 = add2(k, e2, e3);
+  P2 s0 = addp(e0, xe), s2 = addp(e1, e4), s4 = addp(e2, e3);
   P2 m0 = mul2s(s0, HB_P0), m2 = mul2s(s2, HB_P2), m4 = mul2s(s4, HB_P4);
 #ifndef AERODDC_HB_CENTER_MUL
   return fma2(o0, bcast2(HB_P5), add2(k, add2(k, m0, m2), m4));
@@ -135,7 +138,7 @@ __device__ __forceinline__ P2 mix_fast(float a, float b, const float2& s) {
   return fma2(pack2(-s.y, s.x), bcast2(b), mul2s(pack2(s.x, s.y), a));
 }
 __device__ __forceinline__ P2 hb_out_fast(const Ones& k, P2 e0, P2 e1, P2 e2, P2 e3, P2 e4, P2 xe, P2 o0) {
-  const P2 s0 = add2(k, e0, xe), s2 = add2(k, e1, e4), s4 = add2(k, e2, e3);
+  const P2 s0 = addp(e0, xe), s2 = addp(e1, e4), s4 = addp(e2, e3);
   return fma2(s4, bcast2(HB_P4), fma2(o0, bcast2(HB_P5), fma2(s2, bcast2(HB_P2), mul2s(s0, HB_P0))));
 }
 
@@ -185,13 +188,16 @@ struct MainParams {
   float one;                 // 1.0f (see add2)
   int transient;             // tolerance mode: table indices below this use the full recurrence
   int nck;                   // rows of ckpt
-  // A segment is processed as Q consecutive parts of P samples by Q different CTAs chained through HBM:
-  // CTA (q, k) waits for flag[k] == q, loads the state CTA (q-1, k) left in `hand`, and passes it on (flag = q+1).
-  int Q, P, ngroups;
-  int* flags;                // [ngroups][nseg] parts completed; zeroed by the host before every launch
-  int* ticket;               // work-item counter, zeroed by the host before every launch
-  float2* hand;              // [ngroups][nseg][kHandSlots][kThreads]
-  int* err;                  // set to 1 if a chained CTA gave up waiting (should never happen)
+  // A segment of one VFO group is a CHAIN of consecutive parts of P samples, processed by different CTAs that hand the
+  // filter and oscillator state on through `hand`. Which CTA runs which part is decided at run time by a FIFO of ready
+  // chains (see ddc_main_kernel): a CTA that finishes a part appends its chain to the queue, a CTA that starts takes
+  // the chain that has waited longest. Every chain therefore advances at the average pace of all SM slots, whatever the
+  // speed of the individual slot (the warp scheduler favours some resident warps), and all chains end together.
+  int P, ngroups, nchains;   // part length; VFO groups of 32; chains = ngroups * nseg
+  int* sched;                // [0] items taken, [1] queue tail, [2 .. 2+nchains) parts completed per chain, then the queue
+                             // (chain + 1 per entry); zeroed by the host before every launch
+  float2* hand;              // [nchains][kHandSlots][kThreads]
+  int* err;                  // set to 1 if a CTA gave up waiting for its queue entry (should never happen)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -275,6 +281,7 @@ __device__ __forceinline__ void fast_chunk(const Ones& k1, float& oa, float& ob,
 }
 
 __device__ __forceinline__ P2 load_p2(const float2* p) { const float2 v = *p; return pack2(v.x, v.y); }
+__device__ __forceinline__ P2 load_p2_cg(const float2* p) { const float2 v = __ldcg(p); return pack2(v.x, v.y); }   // L2 only: data another CTA wrote during this launch
 __device__ __forceinline__ void store_p2(float2* p, P2 c) { float a, b; unpack2(c, a, b); *p = make_float2(a, b); }
 
 // ---------------------------------------------------------------------------------------------
@@ -372,22 +379,42 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TS::kRawStages * TS::kRawBytes + TS::kCvtBytes);
 
   const int tid = threadIdx.x;
-  // 1-D grid. Work items are numbered [boundary CTA of every VFO group], then part 0 of every (group, segment), then
-  // part 1 of every (group, segment), ... and a CTA takes the next number when it STARTS (atomic ticket), so the
-  // predecessor in its chain has always started before it - whatever order the hardware dispatches blocks in.
-  int bid = 0;
-  if (tid == 0) bid = atomicAdd(p.ticket, 1);
-  bid = __shfl_sync(0xffffffffu, bid, 0);
-  const bool is_boundary = bid < p.ngroups;
-  int q = 0, gy = bid, seg = 0;
-  if (!is_boundary) {
-    bid -= p.ngroups;
-    const int per_q = p.nseg * p.ngroups;
-    q = bid / per_q;
-    const int rem = bid - q * per_q;
-    gy = rem / p.nseg;
-    seg = rem - gy * p.nseg;
+  // 1-D grid of anonymous CTAs; a CTA finds out what it is when it STARTS. Item t (an atomic counter) is: the boundary
+  // role of VFO group t for t < ngroups; part 0 of chain t - ngroups for the next nchains items; after that, entry
+  // t - ngroups - nchains of the ready queue, i.e. the next part of whichever chain was handed on at that position.
+  // Every entry below t has been taken by a CTA that started earlier and is resident or finished, so the entry this
+  // CTA waits for is always on its way - whatever order the hardware dispatches blocks in.
+  // The item travels from lane 0 to the warp through shared memory, not a shuffle: a shared-memory load from a uniform
+  // address is uniform to the compiler, which then keeps loop counters, branches and the broadcast 1.0f of add2 in the
+  // uniform datapath (FFMA2 R, R, UR, R instead of three vector-register operands).
+  __shared__ int s_item[2];
+  if (tid == 0) {
+    int chain = 0, q = 0;
+    const int t = atomicAdd(p.sched, 1);
+    if (t < p.ngroups) {
+      chain = -1 - t;
+    } else if (t < p.ngroups + p.nchains) {
+      chain = t - p.ngroups;
+    } else {
+      const int* entry = p.sched + 2 + p.nchains + (t - p.ngroups - p.nchains);
+      int v, spins = 0;
+      do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(entry) : "memory");
+        if (v == 0) { __nanosleep(100); if (++spins > (1 << 25)) { *p.err = 1; break; } }
+      } while (v == 0);
+      chain = v - 1;                                     // -1 if the watchdog gave up: handled below
+      if (v != 0) q = __ldcg(p.sched + 2 + chain);       // parts of this chain already done (written before the entry)
+      else chain = -1 - p.ngroups;                       // marker: leave
+    }
+    s_item[0] = chain;
+    s_item[1] = q;
   }
+  __syncwarp();
+  const int chain = s_item[0], q = s_item[1];
+  if (chain < -p.ngroups) return;
+  const bool is_boundary = chain < 0;
+  const int gy = is_boundary ? -1 - chain : chain / p.nseg;
+  const int seg = is_boundary ? 0 : chain - gy * p.nseg;
   const int slot = gy * kVfoPerCta + tid;               // this thread's VFO within the slice
   const bool active = slot < p.vfo_count;
   const int vfo = p.vfo_base + (active ? slot : 0);     // inactive lanes shadow VFO 0 of the slice, never store
@@ -401,13 +428,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
   const int seg_end = min(seg_start + p.S, p.B);
   const int part_start = seg_start + q * p.P;
   const int part_end = min(part_start + p.P, seg_end);
-  const bool empty = part_start >= seg_end;               // short last segment: nothing left for this part
   const int warm = (q > 0 || seg == 0) ? 0 : p.W;         // part 0 of segment 0 starts from the saved block history
   const int first = part_start - warm;                    // in-block index of the first sample processed
-  const int total = empty ? 0 : warm + (part_end - part_start);   // multiple of max(kChunk, 2^DA)
+  const int total = warm + (part_end - part_start);       // multiple of max(kChunk, 2^DA)
   const int ntiles = (total + kTile - 1) / kTile;
-  int* flag = p.flags + gy * p.nseg + seg;
-  float2* hand = p.hand + ((size_t)(gy * p.nseg + seg) * kHandSlots) * kThreads + tid;
+  float2* hand = p.hand + ((size_t)chain * kHandSlots) * kThreads + tid;
 
   if (tid == 0) {
     for (int i = 0; i < TS::kRawStages; ++i) mbar_init(&bars[i], 1);
@@ -440,23 +465,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
   const float2* ckpt_col = p.ckpt + vfo;
   HbState hb[kFastStages > 0 ? kFastStages : 1];
   if (q > 0) {
-    // wait for the previous part of this segment, then take over its state
-    if (tid == 0) {
-      const int want = q;
-      int seen, spins = 0;
-      do {
-        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
-        if (seen != want) { __nanosleep(200); if (++spins > (1 << 24)) { *p.err = 1; break; } }
-      } while (seen != want);
-    }
-    __syncwarp();
+    // take over the state the previous part of this chain left behind (lane 0's acquire above + this fence order the loads)
     __threadfence();
 #pragma unroll
     for (int s = 0; s < NF; ++s) {
 #pragma unroll
-      for (int k = 0; k < 5; ++k) hb[s].e[k] = load_p2(hand + (size_t)(s * kStateSlots + k) * kThreads);
+      for (int k = 0; k < 5; ++k) hb[s].e[k] = load_p2_cg(hand + (size_t)(s * kStateSlots + k) * kThreads);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) hb[s].o[k] = load_p2(hand + (size_t)(s * kStateSlots + 5 + k) * kThreads);
+      for (int k = 0; k < 3; ++k) hb[s].o[k] = load_p2_cg(hand + (size_t)(s * kStateSlots + 5 + k) * kThreads);
     }
   } else if (seg == 0) {
 #pragma unroll
@@ -479,15 +495,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
   long long n_abs = p.block_abs + first;
   int idx = (int)(n_abs % p.nco_len);
   float oa, ob;
-  {
+  if (q > 0) {   // the oscillator continues exactly where the previous part stopped
+    const float2 o = __ldcg(hand + (size_t)(kHandSlots - 1) * kThreads);
+    oa = o.x; ob = o.y;
+  } else {       // nearest exact checkpoint, then the recurrence itself up to the first sample
     const int ck = idx / kNcoStride, rem = idx % kNcoStride;
     const float2 c = ckpt_col[(size_t)ck * p.vfo_pitch];
     oa = c.x; ob = c.y;
     for (int i = 0; i < rem; ++i) nco_step(k1, oa, ob, rot);
-  }
-  if (q > 0) {   // the oscillator continues exactly where the previous part stopped
-    const float2 o = hand[(size_t)(kHandSlots - 1) * kThreads];
-    oa = o.x; ob = o.y;
   }
 
   // output cursor in the stage-DA stream: outputs before the part's own start (warm-up) are discarded
@@ -543,23 +558,24 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
     }
   }
 
-  // hand the state to the next part of this segment
-  if (q + 1 < p.Q) {
-    if (!empty || q == 0) {
+  // hand the chain on: state to HBM, then the chain joins the tail of the ready queue
+  if (part_end < seg_end) {
 #pragma unroll
-      for (int s = 0; s < NF; ++s) {
+    for (int s = 0; s < NF; ++s) {
 #pragma unroll
-        for (int k = 0; k < 5; ++k) store_p2(hand + (size_t)(s * kStateSlots + k) * kThreads, hb[s].e[k]);
+      for (int k = 0; k < 5; ++k) store_p2(hand + (size_t)(s * kStateSlots + k) * kThreads, hb[s].e[k]);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) store_p2(hand + (size_t)(s * kStateSlots + 5 + k) * kThreads, hb[s].o[k]);
-      }
-      hand[(size_t)(kHandSlots - 1) * kThreads] = make_float2(oa, ob);
+      for (int k = 0; k < 3; ++k) store_p2(hand + (size_t)(s * kStateSlots + 5 + k) * kThreads, hb[s].o[k]);
     }
+    hand[(size_t)(kHandSlots - 1) * kThreads] = make_float2(oa, ob);
     __threadfence();
     __syncwarp();
     if (tid == 0) {
-      const int done = q + 1;
-      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(done) : "memory");
+      p.sched[2 + chain] = q + 1;
+      const int pos = atomicAdd(p.sched + 1, 1);
+      int* entry = p.sched + 2 + p.nchains + pos;
+      const int v = chain + 1;
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(entry), "r"(v) : "memory");
     }
   }
 }
@@ -577,27 +593,37 @@ struct DeepParams {
   const float2* state_in;     // [kMaxStages][kStateSlots][vfo_pitch]
   float2* const* xd_rows;     // [vfo_pitch] per VFO: where stage-D sample 0 of this block goes
   const unsigned char* vfo_D; // [vfo_pitch]
+  int* counter;               // work-item counter, zeroed by the host before every launch
   int vfo_pitch, mid_pitch, vfo_base, vfo_count;
   int DA;                     // stages already done by the main kernel
   int n_mid;                  // B >> DA
-  int T, Wd, nranges;
+  int T, Wd, nranges, ngroups;
   float one;
 };
 
-constexpr int kDeepWarps = 4;
 constexpr int kDeepWarm = 72;          // 10*(2^3 - 1) input samples reach the last deep stage's history; rounded up to 8
 
+// A persistent grid of one-warp CTAs takes (time range, 32-VFO group) items from a counter. The work is a stream of
+// 8 B per VFO per 32 input samples - bound by memory latency, next to nothing for the FP32 pipe - so the bank launches
+// only a couple of these warps per SM on a high-priority stream: they sit beside the following block's main kernel
+// (which is FP32-bound) instead of displacing it.
 template <bool FAST>
-__global__ void __launch_bounds__(32 * kDeepWarps) ddc_deep_kernel(const DeepParams p) {
-  const int lane = threadIdx.x & 31;
-  const int range = blockIdx.y * kDeepWarps + (threadIdx.x >> 5);
-  if (range >= p.nranges) return;
-  const int slot = blockIdx.x * 32 + lane;
+__global__ void __launch_bounds__(32, 16) ddc_deep_kernel(const DeepParams p) {
+  const int lane = threadIdx.x;
+  Ones k1; k1.one = bcast2(p.one);
+  __shared__ int s_next;
+  for (;;) {
+  __syncwarp();
+  if (lane == 0) s_next = atomicAdd(p.counter, 1);
+  __syncwarp();
+  const int item = s_next;   // through shared memory: uniform to the compiler (see ddc_main_kernel)
+  if (item >= p.nranges * p.ngroups) break;
+  const int range = item / p.ngroups;
+  const int slot = (item - range * p.ngroups) * 32 + lane;
   const bool active = slot < p.vfo_count;
   const int vfo = p.vfo_base + (active ? slot : 0);
   const int D = p.vfo_D[vfo];
   const int nd = max(D - p.DA, 0);                         // 0..3 deep stages for this VFO
-  Ones k1; k1.one = bcast2(p.one);
   HbState hb[kDeepStages];
   const int t0 = range * p.T;
   const int t1 = min(t0 + p.T, p.n_mid);
@@ -624,41 +650,50 @@ __global__ void __launch_bounds__(32 * kDeepWarps) ddc_deep_kernel(const DeepPar
   float2* xd = p.xd_rows[vfo];
   const float2* src = p.mid + (active ? slot : 0);
   // eight input samples at a time while they last (ts and t0 are multiples of 8, so every stage starts a group on its
-  // even phase): 4 / 2 / 1 outputs of deep stage 1 / 2 / 3
+  // even phase): 4 / 2 / 1 outputs of deep stage 1 / 2 / 3. The next group's eight rows are requested before this
+  // group is computed: the kernel is a stream from HBM, and the loads in flight are what sets its speed.
   int t = ts;
-  for (; t + 8 <= t1; t += 8) {
-    float2 in[8];
+  float2 in[8], nx[8];
+  if (t + 8 <= t1) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) in[i] = src[(size_t)(t + i) * p.mid_pitch];
+    for (int i = 0; i < 8; ++i) in[i] = __ldcs(src + (size_t)(t + i) * p.mid_pitch);
+  }
+  for (; t + 8 <= t1; t += 8) {
+    if (t + 16 <= t1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) nx[i] = __ldcs(src + (size_t)(t + 8 + i) * p.mid_pitch);
+    }
     if (nd == 0) {
       if (active && t >= t0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) xd[t + i] = in[i];
       }
-      continue;
-    }
-    P2 y0[4];
+    } else {
+      P2 y0[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) y0[i] = hb_pair<FAST>(k1, hb[0], pack2(in[2 * i].x, in[2 * i].y), pack2(in[2 * i + 1].x, in[2 * i + 1].y));
-    if (nd == 1) {
-      if (active && t >= t0) {
+      for (int i = 0; i < 4; ++i) y0[i] = hb_pair<FAST>(k1, hb[0], pack2(in[2 * i].x, in[2 * i].y), pack2(in[2 * i + 1].x, in[2 * i + 1].y));
+      if (nd == 1) {
+        if (active && t >= t0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) store_p2(xd + (t >> 1) + i, y0[i]);
+          for (int i = 0; i < 4; ++i) store_p2(xd + (t >> 1) + i, y0[i]);
+        }
+      } else {
+        P2 y1[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) y1[i] = hb_pair<FAST>(k1, hb[1], y0[2 * i], y0[2 * i + 1]);
+        if (nd == 2) {
+          if (active && t >= t0) {
+            store_p2(xd + (t >> 2), y1[0]);
+            store_p2(xd + (t >> 2) + 1, y1[1]);
+          }
+        } else {
+          const P2 y2 = hb_pair<FAST>(k1, hb[2], y1[0], y1[1]);
+          if (active && t >= t0) store_p2(xd + (t >> 3), y2);
+        }
       }
-      continue;
     }
-    P2 y1[2];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) y1[i] = hb_pair<FAST>(k1, hb[1], y0[2 * i], y0[2 * i + 1]);
-    if (nd == 2) {
-      if (active && t >= t0) {
-        store_p2(xd + (t >> 2), y1[0]);
-        store_p2(xd + (t >> 2) + 1, y1[1]);
-      }
-      continue;
-    }
-    const P2 y2 = hb_pair<FAST>(k1, hb[2], y1[0], y1[1]);
-    if (active && t >= t0) store_p2(xd + (t >> 3), y2);
+    for (int i = 0; i < 8; ++i) in[i] = nx[i];
   }
   // the last range of a stream whose length is not a multiple of 8 (then no VFO has 3 deep stages): sample by sample
   for (; t < t1; ++t) {
@@ -674,6 +709,7 @@ __global__ void __launch_bounds__(32 * kDeepWarps) ddc_deep_kernel(const DeepPar
     }
     if (!stop && active && t >= t0) store_p2(xd + (t >> nd), x);
   }
+  }   // next item
 }
 
 }  // namespace aeroddc

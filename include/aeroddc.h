@@ -74,7 +74,7 @@ typedef struct aeroddc_segment_plan {
   int warmup;           /* W = 10*2^DA (rounded to the chunk): samples a segment re-processes to rebuild its history */
   int boundary_warmup;  /* 11*2^D: samples the boundary CTA re-processes for the next block's shifted history      */
   int segment_len, n_segments;
-  int parts, part_len;  /* each segment runs as `parts` chained CTAs of part_len samples                           */
+  int parts, part_len;  /* a full segment runs as `parts` chained CTAs of part_len samples (the last one may need fewer) */
   int vfo_groups;       /* CTAs side by side: ceil(n_vfos / 32), one warp of 32 VFOs each                          */
   int ctas;             /* grid size of the launch                                                                 */
 } aeroddc_segment_plan;

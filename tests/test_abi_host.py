@@ -118,6 +118,8 @@ def test_segment_plan_invariants():
             assert p["parts"] >= 1 and p["parts"] * p["part_len"] >= p["segment_len"]
             assert p["segment_len"] >= 4 * p["warmup"]
             assert p["vfo_groups"] == -(-nv // 32)   # one warp of 32 VFOs per CTA
-            assert p["ctas"] == p["vfo_groups"] * (1 + p["parts"] * p["n_segments"])
+            per_group = p["ctas"] // p["vfo_groups"] - 1           # parts of all segments; the last segment may need fewer
+            assert p["ctas"] % p["vfo_groups"] == 0 and p["n_segments"] <= per_group <= p["parts"] * p["n_segments"]
+            assert per_group * p["part_len"] >= blk
     with pytest.raises(aeroddc.AeroDdcError):
         aeroddc.plan_segments(57601, 1, 1)

@@ -148,6 +148,34 @@ def test_gpu_payloads_decode_to_the_identical_acars_set(tmp_path, name):
         assert set(from_gpu[topic]) == expected_records(msgs), topic
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_tolerance_mode_payloads_decode_to_the_identical_acars_set(tmp_path, name):
+    """AERODDC_MODE_FAST (`mode=fast`: fused arithmetic, at most 1 LSB away from the reference's int16) through the
+    unchanged decoder: the record list per topic must equal the CPU chain's and the messages that were sent - the
+    requirement BASELINE.json puts on any output that is not byte-identical."""
+    sc = SCENARIOS[name]
+    iq, sent = _make_capture(tmp_path, sc)
+    gpu, cpu = tmp_path / "gpu", tmp_path / "cpu"
+    gpu.mkdir()
+    subprocess.run([BIN, "-d", "file=%s,format=cu8,mode=fast" % iq, "--dump", str(gpu), sc["ini"]], check=True, capture_output=True)
+    _cpu_dump(sc["ini"], iq, cpu)
+    worst = 0
+    for topic in sc["channels"]:
+        a = np.fromfile(gpu / (topic + ".i16"), np.int16).astype(np.int32)
+        b = np.fromfile(cpu / (topic + ".i16"), np.int16).astype(np.int32)
+        assert a.size == b.size and a.size > 0
+        worst = max(worst, int(np.abs(a - b).max()))
+        err, sig = float(((a - b) ** 2).sum()), float((b ** 2).sum())
+        assert err == 0 or 10 * np.log10(sig / err) >= 80.0, topic      # signals of normal level: the stated SNR bound, unconditionally
+    assert worst <= 3                                                   # 1e-4 of full scale = 3.27 LSB
+    from_gpu = _decode(gpu, sc["bitrate"])
+    from_cpu = _decode(cpu, sc["bitrate"])
+    assert from_gpu == from_cpu
+    for topic, msgs in sent.items():
+        assert set(from_gpu[topic]) == expected_records(msgs), topic
+
+
 def test_restated_viterbi_round_trip_and_error_correction():
     """oracle/viterbi_restated.c stands in for libcorrect (parity unpinned). Known-answer properties a K=7 rate-1/2 decoder
     must have: encode -> decode is the identity (hard and soft), and isolated channel errors are corrected."""

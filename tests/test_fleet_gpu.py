@@ -1,5 +1,6 @@
-"""GPU suite: the native multi-GPU layer (aeroddc_fleet_*): VFO sharding over the node's GPUs with an NCCL
-broadcast of the raw block, from one host thread. On a one-GPU box it checks the degenerate fleet; with two or
+"""GPU suite: the native multi-GPU layer (aeroddc_fleet_*): VFO sharding over the node's GPUs from one host thread, the raw
+block either spread over the GPUs in slices that every kernel reads in place through peer memory (default) or
+broadcast with NCCL (AERODDC_EXCHANGE=nccl). On a one-GPU box it checks the degenerate fleet; with two or
 more GPUs (gpurun --gpus N) it checks that every VFO's bytes equal the single-bank result and the oracle."""
 import numpy as np
 import pytest
@@ -20,12 +21,14 @@ def _descs(fs, n, seed):
     return [dict(mixer=float(rng.integers(int(-0.4 * fs), int(0.4 * fs))), D=[5, 6, 7][i % 3], gain=float(rng.uniform(0.05, 0.4))) for i in range(n)]
 
 
-@pytest.mark.parametrize("ndev", [1, 2, 4, 8])
-def test_fleet_matches_single_bank_and_oracle(ndev):
+@pytest.mark.parametrize("ndev,exchange", [(1, "single"), (2, "peer"), (2, "nccl"), (4, "peer"), (8, "peer"), (8, "nccl")])
+def test_fleet_matches_single_bank_and_oracle(ndev, exchange, monkeypatch):
     import aeroddc
 
     if _ndev() < ndev:
         pytest.skip("needs %d GPUs" % ndev)
+    if exchange == "nccl":
+        monkeypatch.setenv("AERODDC_EXCHANGE", "nccl")
     fs, blk = 1536000, 384000
     descs = _descs(fs, 37, 5)
     fleet = aeroddc.Fleet(fs, blk, aeroddc.CU8, tuple(range(ndev)))
@@ -35,7 +38,7 @@ def test_fleet_matches_single_bank_and_oracle(ndev):
         bank.add_vfo(d["mixer"], d["D"], 0, 0, d["gain"], 1, 1, 1, "F%04d" % i)
     fleet.finalize()
     bank.finalize()
-    assert fleet.num_devices == ndev
+    assert fleet.num_devices == ndev and fleet.exchange == exchange
     assert sorted(set(fleet.device_of(i) for i in range(len(descs)))) == list(range(ndev))
     picks = [0, 1, 17, 36]
     oracles = [Oracle(fs, blk, descs[i]["D"], 0, descs[i]["mixer"], descs[i]["gain"]) for i in picks]

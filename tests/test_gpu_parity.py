@@ -409,3 +409,144 @@ def test_dc_correction_vs_oracle(fmt):
             assert bank.output(i)[0] == o.process(x), (i, b)
     assert abs(float(state[0])) > 1e-4                    # the average really moved
     bank.close()
+
+
+@pytest.mark.parametrize("fmt,slice_len", [(FMT_CF32, 96032), (FMT_CU8, 128000), (FMT_CS16, 191968)])
+def test_sliced_block_equals_whole_block(fmt, slice_len):
+    """aeroddc_bank_submit_device_sliced: the raw block lies in several device buffers (here all on one GPU; on a node one
+    per GPU, read through peer memory). Slice lengths that are not a multiple of the 256-sample tile make tiles straddle
+    two slices (two TMA copies into one tile); the boundary role and every segment must still see the same samples."""
+    a = _aeroddc()
+    fs, blk = 1536000, 384000
+    rng = np.random.default_rng(int(slice_len))
+    vfos = _mixed_bank(fs, 40, rng, [5, 6, 7, 3, 8, 0])
+    whole = make_bank(fs, blk, fmt, vfos)
+    cut = make_bank(fs, blk, fmt, vfos)
+    n_slices = -(-blk // slice_len)
+    bps = {FMT_CU8: 2, FMT_CS16: 4, FMT_CF32: 8}[fmt]
+    ptrs = [a.dev_alloc(0, slice_len * bps) for _ in range(n_slices)]
+    for b in range(3):
+        raw = synth_raw(fmt, b * blk, blk, seed=19, amp=0.8)
+        whole.process(raw)
+        for i, p in enumerate(ptrs):
+            a.dev_upload(0, p, raw[2 * i * slice_len:2 * min((i + 1) * slice_len, blk)])
+        cut.submit_device_sliced(ptrs, slice_len)
+        cut.wait()
+        for i in range(len(vfos)):
+            assert cut.output(i) == whole.output(i), (i, b)
+    with pytest.raises(a.AeroDdcError):
+        cut.submit_device_sliced(ptrs[:-1], slice_len)          # the slices do not cover the block
+    with pytest.raises(a.AeroDdcError):
+        cut.submit_device_sliced(ptrs, slice_len + 8)           # not a multiple of 32
+    for p in ptrs:
+        a.dev_free(0, p)
+    whole.close()
+    cut.close()
+
+
+def test_benchmark_shape_1024_vfos_six_blocks_byte_identical():
+    """The configuration bench.py times (BASELINE configs[3]: 1024 VFOs x 61.44 MS/s cf32, D=8, late /5), with bench.py's own
+    VFO set and its own checker: six consecutive distinct blocks - five block boundaries and the oscillator-table wrap at
+    the start of block 4 - and the first, the last and six other VFOs byte for byte against the reference chain
+    (SURVEY.md section 8d, configs C/D). Also: bank.reset() really rewinds (the replay repeats the bytes)."""
+    import bench
+
+    a = _aeroddc()
+    freqs = bench.vfo_freqs(bench.N_VFOS)
+    bank = a.Bank(bench.FS, bench.BLOCK, a.CF32, 0)
+    for v in range(bench.N_VFOS):
+        bank.add_vfo(float(freqs[v]), bench.DECIM, bench.LATE, 0, bench.GAIN, 1, 1, 1, "V%04d" % v)
+    bank.finalize()
+    n = bench.N_VFOS
+    picks = sorted(set([0, n - 1] + [int(round(i * (n - 1) / 7.0)) for i in range(1, 7)]))
+    blocks = [bench.parity_block(k) for k in range(bench.PARITY_BLOCKS)]
+    got = [[] for _ in picks]
+    for x in blocks:
+        bank.process(x)
+        for j, i in enumerate(picks):
+            got[j].append(bank.output(i)[0])
+    kind, bad = bench.parity_check(blocks, [(bench.DECIM, bench.LATE, float(freqs[i]), bench.GAIN) for i in picks], got)
+    assert not bad, (kind, bad)
+    assert all(any(p) for g in got for p in g)                  # no payload is all zeros: the comparison is not vacuous
+    bank.reset()
+    for k in range(2):
+        bank.process(blocks[k])
+        assert bank.output(picks[-1])[0] == got[-1][k]
+    bank.close()
+
+
+def test_subnormal_inputs_keep_the_payload_bytes():
+    """The half-band centre tap is applied as one fused multiply-add (0.5*w is exact for every normal w). It can differ from
+    the reference's separate product and sum only when w and the running sum are both subnormal - values that end as 0 in
+    every int16 payload. A signal fading from full scale through the subnormal range to zero and back, plus a block that is
+    subnormal throughout: payload bytes stay identical, and so do all stage-D floats of normal magnitude."""
+    fs, blk = 288000, 57600
+    vfos = [dict(mixer=12345.0, D=3, L=0, gain=0.5), dict(mixer=-40000.0, D=1, L=6, gain=0.4), dict(mixer=3000.0, D=5, L=0, gain=1e6)]
+    bank = make_bank(fs, blk, FMT_CF32, vfos)
+    oracles = make_oracles(fs, blk, vfos)
+    t = np.arange(blk, dtype=np.float64) / blk
+    envs = [np.power(10.0, -46.0 * t), np.full(blk, 1e-41), np.power(10.0, -46.0 * (1.0 - t)), np.ones(blk)]
+    tiny_seen = 0
+    for b, env in enumerate(envs):
+        x = synth_raw(FMT_CF32, b * blk, blk, seed=23, amp=0.9).astype(np.float64)
+        x = (x * np.repeat(env, 2)).astype(np.float32)
+        tiny_seen += int(((np.abs(x) > 0) & (np.abs(x) < 1.17e-38)).sum())
+        bank.process(x)
+        for i, o in enumerate(oracles):
+            want = o.process(x)
+            assert bank.output(i)[0] == want, (i, b)
+            sg = bank.stage_d(i, blk >> vfos[i]["D"])
+            so = o.stage(vfos[i]["D"])
+            big = np.abs(so) > 1e-30
+            assert np.array_equal(sg[big], so[big]), (i, b)
+    assert tiny_seen > 1000          # the input really went through the subnormal range
+    bank.close()
+
+
+def _worst_rotation(fs, lo, hi):
+    """The integer frequency in [lo, hi) whose float32 rotation (cos, sin) is furthest from unit length."""
+    a = _aeroddc()
+    best, bf = -1.0, lo
+    for f in range(lo, hi):
+        c, s = a.design_rotation(float(fs), float(f))
+        d = abs(float(np.float32(c)) ** 2 + float(np.float32(s)) ** 2 - 1.0)
+        if d > best:
+            best, bf = d, f
+    return float(bf), best
+
+
+@pytest.mark.parametrize("fs,blk,D,late", [(250000, 51200, 8, 5), (288000 - 16, 57568, 1, 0)])
+def test_fast_mode_worst_case_rotation_and_misaligned_table(fs, blk, D, late):
+    """Tolerance mode where it is weakest: a table length that is not a multiple of the 32-sample chunk (after the first
+    restart every checkpoint stride boundary falls inside a chunk) and the frequency whose float32 rotation is furthest
+    from unit length (the rotation-only oscillator drifts fastest between exact checkpoints). Bounds as stated in
+    include/aeroddc.h: max |err| <= 1e-4 of full scale; error SNR >= 80 dB on this signal of normal level, unconditionally."""
+    a = _aeroddc()
+    f, dev = _worst_rotation(fs, 20000, 24000)
+    assert dev > 3e-8
+    bank = a.Bank(fs, blk, a.CF32, 0)
+    bank.add_vfo(f, D, late, 0, 0.3, 1, 1, 1, "FWORS")
+    bank.set_mode(a.MODE_FAST)
+    bank.finalize()
+    o = Oracle(fs, blk, D, late, f, 0.3, 0)
+    k = np.arange(blk, dtype=np.float64)
+    for b in range(2 * fs // blk + 3):           # two table restarts and more
+        n = b * blk + k
+        x = synth_raw(FMT_CF32, b * blk, blk, seed=4, amp=0.2)
+        delta = 0.2 * fs / (1 << D) / max(late, 1)                # a carrier inside the audio band after the mix, whichever
+        for fc in (-f + delta, f + delta):                        # way round the mixer's sign convention is
+            ph = 2 * np.pi * ((fc / fs * n) % 1.0)
+            x[0::2] += (0.3 * np.cos(ph)).astype(np.float32)
+            x[1::2] += (0.3 * np.sin(ph)).astype(np.float32)
+        bank.process(x)
+        want = np.frombuffer(o.process(x), np.int16)
+        got = np.frombuffer(bank.output(0)[0], np.int16)
+        maxerr, snr = parity_metrics(got, want)
+        assert maxerr <= 1e-4, (b, maxerr)
+        if b > 0:
+            assert float(np.sqrt((want.astype(np.float64) ** 2).mean())) > 1000.0     # normal level
+            assert snr >= 80.0, (b, snr)
+            sg = bank.stage_d(0, blk >> D).astype(np.float64)
+            so = o.stage(D).astype(np.float64)
+            assert 10 * np.log10((so * so).sum() / max(((sg - so) ** 2).sum(), 1e-300)) >= 95.0, b
+    bank.close()
