@@ -418,7 +418,6 @@ def main():
     gloo = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
         gloo = dist.new_group(backend="gloo")          # host-side barriers that launch nothing on the GPUs
 
