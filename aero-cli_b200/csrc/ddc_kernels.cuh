@@ -151,12 +151,20 @@ __device__ __forceinline__ P2 hb_even(const Ones& k, HbState& h, P2 xe) {
   return y;
 }
 __device__ __forceinline__ void hb_odd(HbState& h, P2 xo) { h.o[0] = h.o[1]; h.o[1] = h.o[2]; h.o[2] = xo; }
+// the same, also remembering the three odd-phase samples that fall out of h.o (deep kernel: saved block-end history)
+template <bool FAST>
+__device__ __forceinline__ P2 deep_pair(const Ones& k, HbState& h, P2 (&ox)[3], P2 xe, P2 xo);
 // consume the pair (x[2j], x[2j+1]) and return output j
 template <bool FAST>
 __device__ __forceinline__ P2 hb_pair(const Ones& k, HbState& h, P2 xe, P2 xo) {
   const P2 y = hb_even<FAST>(k, h, xe);
   hb_odd(h, xo);
   return y;
+}
+template <bool FAST>
+__device__ __forceinline__ P2 deep_pair(const Ones& k, HbState& h, P2 (&ox)[3], P2 xe, P2 xo) {
+  ox[0] = ox[1]; ox[1] = ox[2]; ox[2] = h.o[0];
+  return hb_pair<FAST>(k, h, xe, xo);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -175,15 +183,15 @@ struct MainParams {
   const float2* qlast;       // [vfo_pitch] q[L-1], the value sample 0 is mixed with
   const float2* state_in;    // [kMaxStages][kStateSlots][vfo_pitch] history at the start of this block
   float2* state_out;         // same layout, history for the start of the next block
-  const unsigned char* vfo_D; // [vfo_pitch] half-band stages of each VFO (the boundary role rebuilds all of them)
-  float2* mid;               // [B >> DA][mid_pitch] output: the stage-DA stream of this block, VFO (of this launch) fastest
-  int mid_pitch;
+  float2* mid;               // [ngroups][B >> DA][32] output: the stage-DA stream of this block, one contiguous run of 256-byte
+  int n_mid;                 // rows per 32-VFO group (n_mid = B >> DA rows), so that writer and reader both stream sequentially.
+  float2* const* xd_rows;    // mid == NULL (no VFO of the launch has a deep stage and the bank runs its kernels in order):
+                             // the samples go straight into the per-VFO stage-D rows ([vfo_pitch] pointers)
   long long block_abs;       // absolute index of the block's first sample
   int vfo_pitch;             // padded VFO count (row pitch of ckpt/rot/state/mid)
   int vfo_base, vfo_count;   // VFO slice handled by this launch (all share DA = min(D, 5))
   int DA;                    // half-band stages of this kernel
   int B, S, W, nseg;         // block length, segment length, warm-up length, segments per block
-  int Wb;                    // warm-up of the boundary role: 11*2^Dmax (it needs 11 samples of history per stage)
   int nco_len;               // L = (int)Fs, the oscillator table length
   float one;                 // 1.0f (see add2)
   int transient;             // tolerance mode: table indices below this use the full recurrence
@@ -285,75 +293,119 @@ __device__ __forceinline__ P2 load_p2_cg(const float2* p) { const float2 v = __l
 __device__ __forceinline__ void store_p2(float2* p, P2 c) { float a, b; unpack2(c, a, b); *p = make_float2(a, b); }
 
 // ---------------------------------------------------------------------------------------------
-// Boundary role: recompute, from the last Wb samples of this block, the history every stage of
-// every VFO will see at the start of the NEXT block. The reference re-seeds each half-band queue
-// with queue[n-1 .. n+9] instead of the last 11 samples (FIR::FIRQueueBackToFront, dsp.cpp:163-172):
-// history index l<0 of the next block is this block's sample n-1+l, so the newest sample x[n-1]
-// is dropped and the window is one sample older than the true one. In polyphase terms the next
-// block's even-phase history is this block's odd samples o[n/2-6 .. n/2-2] and its odd-phase
-// history is this block's even samples e[n/2-3 .. n/2-1].
-// Straightforward per-thread code with local-memory rings; it runs on one extra CTA per 32 VFOs
-// concurrently with the segment CTAs (it takes the first tickets), so its speed does not matter.
-// VFOs of one launch may differ in D (they share min(D, 5)): every thread walks the same Wb = 11*2^Dmax samples -
-// a longer run-in than its own 11*2^D leaves the same final history - with its own stage count.
+// Boundary role: recompute, from the last Wb samples of this block, the history the register stages of every VFO will
+// see at the start of the NEXT block. The reference re-seeds each half-band queue with queue[n-1 .. n+9] instead of the
+// last 11 samples (FIR::FIRQueueBackToFront, dsp.cpp:163-172): history index l<0 of the next block is this block's
+// sample n-1+l, so the newest sample x[n-1] is dropped and the window is one sample older than the true one. In
+// polyphase terms the next block's even-phase history is this block's odd samples x[n-11], x[n-9] .. x[n-3] and its
+// odd-phase history is this block's even samples x[n-6], x[n-4], x[n-2] (n = the stage's input count, even).
+// One extra CTA per 32 VFOs runs the ordinary register cascade over the last 11*2^NF samples (zero history in front:
+// 10*(2^NF - 1) samples of run-in, then 12 valid inputs of the last stage) and keeps the last 12 inputs of every stage.
+// The stages beyond the register cascade get their history from the deep kernel, which sees the end of their streams.
 // ---------------------------------------------------------------------------------------------
-template <int FMT, bool FAST>
-__device__ void boundary_role(const MainParams& p, int vfo, bool active) {
-  P2 eh[kMaxStages][5];
-  P2 oh[kMaxStages][6];
-#pragma unroll 1
-  for (int s = 0; s < kMaxStages; ++s) {
-    for (int k = 0; k < 5; ++k) eh[s][k] = pzero();
-    for (int k = 0; k < 6; ++k) oh[s][k] = pzero();
+template <int M> __device__ __forceinline__ void keep_last12(P2 (&h)[12], const P2* in) {   // M new inputs, oldest first
+  if (M >= 12) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) h[k] = in[M - 12 + k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 12 - M; ++k) h[k] = h[k + M];
+#pragma unroll
+    for (int k = 0; k < M; ++k) h[12 - M + k] = in[k];
+  }
+}
+
+template <int NF, int FMT, bool FAST>
+__device__ void boundary_role(const MainParams& p, int vfo, bool active, float2* tile) {
+  if (NF == 0) return;                                  // no half-band stage in this kernel: nothing to save
+  constexpr int NS = NF > 0 ? NF : 1;
+  P2 last[NS][12];
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int k = 0; k < 12; ++k) last[s][k] = pzero();
+  HbState hb[kFastStages > 0 ? kFastStages : 1];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) hb[s].e[k] = pzero();
+#pragma unroll
+    for (int k = 0; k < 3; ++k) hb[s].o[k] = pzero();
   }
   Ones k1; k1.one = bcast2(p.one);
   const float2 r = p.rot[vfo];
   Rot rot; rot.a = pack2(r.x, r.y); rot.b = pack2(-r.y, r.x);
   const float2 ql = p.qlast[vfo];
-  const int D = p.vfo_D[vfo];
-  const int start = p.B - p.Wb;                      // in-block index of the first warm-up sample
-  const long long n0 = p.block_abs + start;
-  int idx = (int)(n0 % p.nco_len);
+  const float2* ckpt_col = p.ckpt + vfo;
+  const int Wb = ((11 << NF) + kChunk - 1) / kChunk * kChunk;
+  const int start = p.B - Wb;                           // in-block index of the first run-in sample (>= 0: blocks hold >= 20*2^D samples)
+  long long n_abs = p.block_abs + start;
+  int idx = (int)(n_abs % p.nco_len);
   float oa, ob;
   {
     const int ck = idx / kNcoStride, rem = idx % kNcoStride;
-    const float2 c = p.ckpt[(size_t)ck * p.vfo_pitch + vfo];
+    const float2 c = ckpt_col[(size_t)ck * p.vfo_pitch];
     oa = c.x; ob = c.y;
     for (int i = 0; i < rem; ++i) nco_step(k1, oa, ob, rot);
   }
-  for (int i = 0; i < p.Wb; ++i) {
-    const float2 cd = load_raw_block<FMT>(p.raw, start + i);
-    if (idx == p.nco_len) { idx = 0; oa = 1.0f; ob = 0.0f; }
-    if (FAST && (idx % kNcoStride) == 0) { const float2 c = p.ckpt[(size_t)(idx / kNcoStride) * p.vfo_pitch + vfo]; oa = c.x; ob = c.y; }
-    if (!FAST) nco_step(k1, oa, ob, rot);
-    else if (idx < p.transient) nco_step_fused(oa, ob, rot);
-    else nco_rotate_fast(oa, ob, rot);
-    float a = oa, b = ob;
-    if (n0 + i == 0) { a = ql.x; b = ql.y; }
-    idx++;
-    P2 x = FAST ? mix_fast(a, b, cd) : mix(k1, a, b, cd);
-    int cnt = i;
 #pragma unroll 1
-    for (int s = 0; s < D; ++s) {
-      if (cnt & 1) {
-        for (int k = 0; k < 5; ++k) oh[s][k] = oh[s][k + 1];
-        oh[s][5] = x;
-        break;
+  for (int c = 0; c < Wb; c += kChunk) {
+    __syncwarp();
+    tile[threadIdx.x] = load_raw_block<FMT>(p.raw, start + c + (int)threadIdx.x);   // kThreads == kChunk: one sample per lane
+    __syncwarp();
+    // the chunk, as fast_chunk<NF, true, FAST> runs it, with every stage's inputs kept
+    P2 x0[kChunk];
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) {
+      const float2 sm = tile[i];
+      if (idx == p.nco_len) { idx = 0; oa = 1.0f; ob = 0.0f; }
+      if (FAST && idx >= p.transient && (idx % kNcoStride) == 0) {
+        const float2 c0 = ckpt_col[(size_t)(idx / kNcoStride) * p.vfo_pitch];
+        oa = c0.x; ob = c0.y;
       }
-      const P2 y = FAST ? hb_out_fast(k1, eh[s][0], eh[s][1], eh[s][2], eh[s][3], eh[s][4], x, oh[s][3])
-                        : hb_out(k1, eh[s][0], eh[s][1], eh[s][2], eh[s][3], eh[s][4], x, oh[s][3]);
-      for (int k = 0; k < 4; ++k) eh[s][k] = eh[s][k + 1];
-      eh[s][4] = x;
-      x = y;
-      cnt >>= 1;
+      if (!FAST) nco_step(k1, oa, ob, rot);
+      else if (idx < p.transient) nco_step_fused(oa, ob, rot);
+      else nco_rotate_fast(oa, ob, rot);
+      float a = oa, b = ob;
+      if (n_abs + i == 0) { a = ql.x; b = ql.y; }
+      idx++;
+      x0[i] = FAST ? mix_fast(a, b, sm) : mix(k1, a, b, sm);
+    }
+    n_abs += kChunk;
+    keep_last12<kChunk>(last[0], x0);
+    if (NF > 1) {
+      P2 y0[kChunk / 2];
+#pragma unroll
+      for (int j = 0; j < kChunk / 2; ++j) y0[j] = hb_pair<FAST>(k1, hb[0], x0[2 * j], x0[2 * j + 1]);
+      keep_last12<kChunk / 2>(last[NS > 1 ? 1 : 0], y0);
+      if (NF > 2) {
+        P2 y1[kChunk / 4];
+#pragma unroll
+        for (int j = 0; j < kChunk / 4; ++j) y1[j] = hb_pair<FAST>(k1, hb[1], y0[2 * j], y0[2 * j + 1]);
+        keep_last12<kChunk / 4>(last[NS > 2 ? 2 : 0], y1);
+        if (NF > 3) {
+          P2 y2[kChunk / 8];
+#pragma unroll
+          for (int j = 0; j < kChunk / 8; ++j) y2[j] = hb_pair<FAST>(k1, hb[2], y1[2 * j], y1[2 * j + 1]);
+          keep_last12<kChunk / 8>(last[NS > 3 ? 3 : 0], y2);
+          if (NF > 4) {
+            P2 y3[kChunk / 16];
+#pragma unroll
+            for (int j = 0; j < kChunk / 16; ++j) y3[j] = hb_pair<FAST>(k1, hb[3], y2[2 * j], y2[2 * j + 1]);
+            keep_last12<kChunk / 16>(last[NS > 4 ? 4 : 0], y3);
+          }
+        }
+      }
     }
   }
   if (active) {
-#pragma unroll 1
-    for (int s = 0; s < D; ++s) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
       float2* st = p.state_out + (size_t)s * kStateSlots * p.vfo_pitch + vfo;
-      for (int k = 0; k < 5; ++k) store_p2(st + (size_t)k * p.vfo_pitch, oh[s][k]);            // o[n/2-6 .. n/2-2]
-      for (int k = 0; k < 3; ++k) store_p2(st + (size_t)(5 + k) * p.vfo_pitch, eh[s][2 + k]);  // e[n/2-3 .. n/2-1]
+#pragma unroll
+      for (int k = 0; k < 5; ++k) store_p2(st + (size_t)k * p.vfo_pitch, last[s][1 + 2 * k]);        // x[n-11], x[n-9] .. x[n-3]
+#pragma unroll
+      for (int k = 0; k < 3; ++k) store_p2(st + (size_t)(5 + k) * p.vfo_pitch, last[s][6 + 2 * k]);  // x[n-6], x[n-4], x[n-2]
     }
   }
 }
@@ -384,9 +436,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
   // t - ngroups - nchains of the ready queue, i.e. the next part of whichever chain was handed on at that position.
   // Every entry below t has been taken by a CTA that started earlier and is resident or finished, so the entry this
   // CTA waits for is always on its way - whatever order the hardware dispatches blocks in.
-  // The item travels from lane 0 to the warp through shared memory, not a shuffle: a shared-memory load from a uniform
-  // address is uniform to the compiler, which then keeps loop counters, branches and the broadcast 1.0f of add2 in the
-  // uniform datapath (FFMA2 R, R, UR, R instead of three vector-register operands).
+  // The item travels from lane 0 to the warp through shared memory: a shared-memory load from a uniform address is
+  // uniform to the compiler, so the loop counters and branches below stay in the uniform datapath.
   __shared__ int s_item[2];
   if (tid == 0) {
     int chain = 0, q = 0;
@@ -420,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
   const int vfo = p.vfo_base + (active ? slot : 0);     // inactive lanes shadow VFO 0 of the slice, never store
 
   if (is_boundary) {
-    boundary_role<FMT, FAST>(p, vfo, active);
+    boundary_role<NF, FMT, FAST>(p, vfo, active, reinterpret_cast<float2*>(raw));
     return;
   }
 
@@ -506,7 +557,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
   }
 
   // output cursor in the stage-DA stream: outputs before the part's own start (warm-up) are discarded
-  float2* mid = p.mid + (active ? slot : 0);
+  float2* mid = p.mid ? p.mid + (size_t)gy * p.n_mid * 32 + tid : p.xd_rows[vfo];
+  const size_t mid_stride = p.mid ? (size_t)32 : (size_t)1;
   const int out_first = part_start >> NF;                 // first stage-DA index this part owns
   int out_pos = first >> NF;                              // stage-DA index of the next output produced
   float2 nxt = make_float2(0.f, 0.f);                     // tolerance mode: prefetched checkpoint of stride nxt_k
@@ -548,7 +600,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
       n_abs += kChunk;
 #pragma unroll
       for (int i = 0; i < (kChunk >> NF); ++i) {
-        if (out_pos >= out_first && active) store_p2(mid + (size_t)out_pos * p.mid_pitch, out[i]);   // 32 lanes: one 256-byte row
+        if (out_pos >= out_first && active) store_p2(mid + (size_t)out_pos * mid_stride, out[i]);   // mid stream: 32 lanes write one 256-byte row
         out_pos++;
       }
     }
@@ -584,31 +636,35 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
 // Deep kernel: half-band stages DA .. D-1 of every VFO of one launch group, from the stage-DA stream the main kernel
 // wrote ([time][VFO], so a warp's 32 VFOs read one 256-byte row per time step), to the per-VFO stage-D rows the
 // tail kernel reads. One warp = 32 VFOs x one range of T input samples, history in registers; ranges after the first
-// run in over Wd = 10*(2^3 - 1) (rounded to 8) earlier samples with zero history and discard those outputs; range 0
+// run in over Wd = 10*(2^3 - 1) (rounded up to 96) earlier samples with zero history and discard those outputs; range 0
 // starts from the block's saved (shifted, see boundary_role) history. A VFO with D <= 5 has no deep stage: its
 // samples are only moved into its row. Lanes of a warp may differ in their stage count.
 // ---------------------------------------------------------------------------------------------
 struct DeepParams {
-  const float2* mid;          // [n_mid][mid_pitch]
-  const float2* state_in;     // [kMaxStages][kStateSlots][vfo_pitch]
+  const float2* mid;          // [ngroups][n_mid][32]
+  const float2* state_in;     // [kMaxStages][kStateSlots][vfo_pitch] history at the start of this block
+  float2* state_out;          // same layout: the warp that reaches the end of the stream saves the deep stages' history
   float2* const* xd_rows;     // [vfo_pitch] per VFO: where stage-D sample 0 of this block goes
-  const unsigned char* vfo_D; // [vfo_pitch]
+  const unsigned char* vfo_D; // [vfo_pitch] half-band stages of each VFO
   int* counter;               // work-item counter, zeroed by the host before every launch
-  int vfo_pitch, mid_pitch, vfo_base, vfo_count;
+  int vfo_pitch, vfo_base, vfo_count;
   int DA;                     // stages already done by the main kernel
   int n_mid;                  // B >> DA
   int T, Wd, nranges, ngroups;
   float one;
 };
 
-constexpr int kDeepWarm = 72;          // 10*(2^3 - 1) input samples reach the last deep stage's history; rounded up to 8
+constexpr int kDeepStep = 32;          // input samples per unrolled step of the deep kernel; its cp.async ring holds two steps (16 KB per warp)
+constexpr int kDeepWarm = 96;          // 10*(2^3 - 1) input samples reach the last deep stage's history; rounded up to a step
+constexpr int kDeepCtasPerSm = 12;     // 12 x 16 KB of ring per SM; up to 168 registers per thread
 
 // A persistent grid of one-warp CTAs takes (time range, 32-VFO group) items from a counter. The work is a stream of
 // 8 B per VFO per 32 input samples - bound by memory latency, next to nothing for the FP32 pipe - so the bank launches
 // only a couple of these warps per SM on a high-priority stream: they sit beside the following block's main kernel
 // (which is FP32-bound) instead of displacing it.
 template <bool FAST>
-__global__ void __launch_bounds__(32, 16) ddc_deep_kernel(const DeepParams p) {
+__global__ void __launch_bounds__(32, kDeepCtasPerSm) ddc_deep_kernel(const DeepParams p) {
+  extern __shared__ __align__(16) float2 ring[];   // [2][kDeepStep][32]
   const int lane = threadIdx.x;
   Ones k1; k1.one = bcast2(p.one);
   __shared__ int s_next;
@@ -625,10 +681,16 @@ __global__ void __launch_bounds__(32, 16) ddc_deep_kernel(const DeepParams p) {
   const int D = p.vfo_D[vfo];
   const int nd = max(D - p.DA, 0);                         // 0..3 deep stages for this VFO
   HbState hb[kDeepStages];
+  P2 ox[kDeepStages][3];                                   // the three odd-phase samples before hb[s].o[0] (for the saved history)
+#pragma unroll
+  for (int s = 0; s < kDeepStages; ++s)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ox[s][k] = pzero();
   const int t0 = range * p.T;
   const int t1 = min(t0 + p.T, p.n_mid);
-  const int ts = range == 0 ? 0 : t0 - p.Wd;
-  if (range == 0) {
+  const bool from_start = t0 <= p.Wd;                      // the run-in would reach the block start: begin there, with the saved history
+  const int ts = from_start ? 0 : t0 - p.Wd;
+  if (from_start) {
 #pragma unroll
     for (int s = 0; s < kDeepStages; ++s) {
       const int st_i = min(p.DA + s, kMaxStages - 1);
@@ -648,66 +710,96 @@ __global__ void __launch_bounds__(32, 16) ddc_deep_kernel(const DeepParams p) {
     }
   }
   float2* xd = p.xd_rows[vfo];
-  const float2* src = p.mid + (active ? slot : 0);
-  // eight input samples at a time while they last (ts and t0 are multiples of 8, so every stage starts a group on its
-  // even phase): 4 / 2 / 1 outputs of deep stage 1 / 2 / 3. The next group's eight rows are requested before this
-  // group is computed: the kernel is a stream from HBM, and the loads in flight are what sets its speed.
+  const float2* src = p.mid + (size_t)(item - range * p.ngroups) * p.n_mid * 32 + lane;
+  // kDeepStep (32) input samples at a time while they last (ts and t0 are multiples of 32, so every stage starts a step
+  // on its even phase): 16 / 8 / 4 outputs of deep stage 1 / 2 / 3, fully unrolled so that the filter histories are
+  // renamed rather than moved. The kernel is a stream from HBM and the bytes in flight set its speed: every lane copies
+  // its own samples one step ahead with cp.async into a two-step shared-memory ring (lane-private slots, so no barrier is
+  // needed - only the lane's own wait_group).
   int t = ts;
-  float2 in[8], nx[8];
-  if (t + 8 <= t1) {
+  const int nstep = (t1 - ts) / kDeepStep;
+  auto fetch = [&](int g) {
+    if (g < nstep) {
+      float2* dst = ring + ((g & 1) * kDeepStep) * 32 + lane;
+      const float2* from = src + (size_t)(ts + kDeepStep * g) * 32;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) in[i] = __ldcs(src + (size_t)(t + i) * p.mid_pitch);
-  }
-  for (; t + 8 <= t1; t += 8) {
-    if (t + 16 <= t1) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) nx[i] = __ldcs(src + (size_t)(t + 8 + i) * p.mid_pitch);
+      for (int i = 0; i < kDeepStep; ++i)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst + i * 32)), "l"(from + i * 32) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");   // an empty group keeps the count uniform
+  };
+  fetch(0);
+  for (int g = 0; g < nstep; ++g, t += kDeepStep) {
+    fetch(g + 1);                                                  // into the slot step g-1 occupied
+    asm volatile("cp.async.wait_group 1;" ::: "memory");           // step g has landed
+    const float2* got = ring + ((g & 1) * kDeepStep) * 32 + lane;
+    const bool keep = active && t >= t0;
     if (nd == 0) {
-      if (active && t >= t0) {
+      if (keep) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) xd[t + i] = in[i];
+        for (int i = 0; i < kDeepStep; ++i) xd[t + i] = got[i * 32];
       }
-    } else {
-      P2 y0[4];
+      continue;
+    }
+    P2 y0[kDeepStep / 2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) y0[i] = hb_pair<FAST>(k1, hb[0], pack2(in[2 * i].x, in[2 * i].y), pack2(in[2 * i + 1].x, in[2 * i + 1].y));
-      if (nd == 1) {
-        if (active && t >= t0) {
+    for (int i = 0; i < kDeepStep / 2; ++i) {
+      const float2 a = got[(2 * i) * 32], c = got[(2 * i + 1) * 32];
+      y0[i] = deep_pair<FAST>(k1, hb[0], ox[0], pack2(a.x, a.y), pack2(c.x, c.y));
+    }
+    if (nd == 1) {
+      if (keep) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) store_p2(xd + (t >> 1) + i, y0[i]);
-        }
-      } else {
-        P2 y1[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) y1[i] = hb_pair<FAST>(k1, hb[1], y0[2 * i], y0[2 * i + 1]);
-        if (nd == 2) {
-          if (active && t >= t0) {
-            store_p2(xd + (t >> 2), y1[0]);
-            store_p2(xd + (t >> 2) + 1, y1[1]);
-          }
-        } else {
-          const P2 y2 = hb_pair<FAST>(k1, hb[2], y1[0], y1[1]);
-          if (active && t >= t0) store_p2(xd + (t >> 3), y2);
-        }
+        for (int i = 0; i < kDeepStep / 2; ++i) store_p2(xd + (t >> 1) + i, y0[i]);
       }
+      continue;
+    }
+    P2 y1[kDeepStep / 4];
+#pragma unroll
+    for (int i = 0; i < kDeepStep / 4; ++i) y1[i] = deep_pair<FAST>(k1, hb[1], ox[1], y0[2 * i], y0[2 * i + 1]);
+    if (nd == 2) {
+      if (keep) {
+#pragma unroll
+        for (int i = 0; i < kDeepStep / 4; ++i) store_p2(xd + (t >> 2) + i, y1[i]);
+      }
+      continue;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) in[i] = nx[i];
+    for (int i = 0; i < kDeepStep / 8; ++i) {
+      const P2 y2 = deep_pair<FAST>(k1, hb[2], ox[2], y1[2 * i], y1[2 * i + 1]);
+      if (keep) store_p2(xd + (t >> 3) + i, y2);
+    }
   }
-  // the last range of a stream whose length is not a multiple of 8 (then no VFO has 3 deep stages): sample by sample
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // the last range of a stream whose length is not a multiple of 32: sample by sample
   for (; t < t1; ++t) {
-    P2 x = load_p2(src + (size_t)t * p.mid_pitch);
+    P2 x = load_p2(src + (size_t)t * 32);
     int cnt = t;
     bool stop = false;
 #pragma unroll
     for (int s = 0; s < kDeepStages; ++s) {
       if (!stop && s < nd) {
-        if (cnt & 1) { hb_odd(hb[s], x); stop = true; }
+        if (cnt & 1) { ox[s][0] = ox[s][1]; ox[s][1] = ox[s][2]; ox[s][2] = hb[s].o[0]; hb_odd(hb[s], x); stop = true; }
         else { x = hb_even<FAST>(k1, hb[s], x); cnt >>= 1; }
       }
     }
     if (!stop && active && t >= t0) store_p2(xd + (t >> nd), x);
+  }
+  // end of the stream: the shifted history the deep stages start the next block from (see boundary_role)
+  if (t1 == p.n_mid && active) {
+#pragma unroll
+    for (int s = 0; s < kDeepStages; ++s) {
+      if (s < nd) {
+        float2* st = p.state_out + (size_t)(p.DA + s) * kStateSlots * p.vfo_pitch + vfo;
+        store_p2(st, ox[s][0]);                                                      // x[n-11]
+        store_p2(st + (size_t)1 * p.vfo_pitch, ox[s][1]);                            // x[n-9]
+        store_p2(st + (size_t)2 * p.vfo_pitch, ox[s][2]);                            // x[n-7]
+        store_p2(st + (size_t)3 * p.vfo_pitch, hb[s].o[0]);                          // x[n-5]
+        store_p2(st + (size_t)4 * p.vfo_pitch, hb[s].o[1]);                          // x[n-3]
+#pragma unroll
+        for (int k = 0; k < 3; ++k) store_p2(st + (size_t)(5 + k) * p.vfo_pitch, hb[s].e[2 + k]);   // x[n-6], x[n-4], x[n-2]
+      }
+    }
   }
   }   // next item
 }

@@ -4,7 +4,7 @@
 // streams/events, and the launches of the kernels in ddc_kernels.cuh / aux_kernels.cuh.
 // Replaces the per-VFO objects of /root/reference/publish/vfo.cpp:57-139 (init) and the block pump
 // of /root/reference/publish/publisher.cpp:285-306 (demodData -> vfo::process for every VFO).
-#include "../../include/aeroddc.h"
+#include "../include/aeroddc.h"
 
 #include <algorithm>
 #include <cmath>
@@ -12,12 +12,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <string>
 #include <vector>
 
-#include "ddc_kernels.cuh"
 #include "aux_kernels.cuh"
+#include "ddc_kernels.cuh"
 #include "design.h"
 
 namespace {
@@ -68,36 +67,15 @@ struct VfoRec {
   size_t hil_idx_off;
 };
 
-struct Group {   // VFOs sharing input stream and DA = min(D, 5): one launch of the main and of the deep kernel per block
+struct Group {   // VFOs sharing input stream and D: one launch of the main kernel per block
   int parent;      // -1: raw IQ of the bank; else the VFO whose stage-D stream is the input
-  int DA, Dmax, base, count;
+  int D, base, count;
   int fs_in, blk_in;
   int S, W, Wb, nseg;
-  int Q, P;          // parts per full segment and part length (chained CTAs, see ddc_kernels.cuh)
-  int nchains, nparts; // chains = 32-VFO groups x segments; parts of all chains together (the last segment may be shorter)
-  bool direct;       // no VFO of the group has a deep stage and the bank runs in order: the main kernel writes the stage-D rows itself
-  int mid_pitch;     // lanes of the stage-DA stream: 32 per VFO group
-  int n_mid;         // stage-DA samples per block
-  int deep_T, deep_ranges;
-  int* d_sched = nullptr;      // [2 + nchains + (nparts - nchains)] scheduler words of the main kernel
-  size_t sched_words = 0;
+  int Q, P;          // parts per segment and part length (chained CTAs, see ddc_kernels.cuh)
+  int* d_flags = nullptr;
   float2* d_hand = nullptr;
-  float2* d_mid[2] = {nullptr, nullptr};   // [32-VFO group][n_mid][32], by block parity
 };
-
-// cudaFuncSetAttribute is state of the (function, device) pair, shared by every bank of the process: a second bank with
-// shorter filters must not shrink the limit under a first bank that needs more (the reference's own Publisher builds one
-// private bank per main VFO when it drives the product's vfo class, INTEGRATION.md option C). Keep the maximum ever asked.
-cudaError_t raise_tail_smem_limit(int device, size_t bytes) {
-  static std::mutex mu;
-  static size_t limit[64] = {};
-  std::lock_guard<std::mutex> lock(mu);
-  const int d = device & 63;
-  if (bytes <= limit[d]) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  if (e == cudaSuccess) limit[d] = bytes;
-  return e;
-}
 
 int raw_bytes(int fmt) { return fmt == AERODDC_CU8 ? 2 : (fmt == AERODDC_CS16 ? 4 : 8); }
 
@@ -114,12 +92,8 @@ struct aeroddc_bank {
   bool finalized = false;
   int mode = AERODDC_MODE_EXACT;
   bool dcc = false;
-  float* d_dcc_out[2] = {nullptr, nullptr};   // DC-corrected cf32 block, by block parity (block k+1 is corrected while block k computes)
+  float* d_dcc_out = nullptr;    // DC-corrected cf32 block
   float* d_dcc_state = nullptr;  // running average per rail
-  size_t dcc_smem = 0;           // dynamic shared memory the DC kernel asks for (a whole SM's worth, see enqueue_block)
-  bool nested = false;           // some VFO feeds sub-VFOs, or some group needs no deep kernel: the kernels of a block then run
-                                 // strictly in order on one stream (no overlap with the next block's main kernel)
-  bool poisoned = false;         // a chained CTA gave up waiting: every later call fails
   std::vector<VfoRec> vfos;
   std::vector<Group> groups;
   int vfo_pitch = 0;
@@ -128,14 +102,10 @@ struct aeroddc_bank {
 
   // device memory
   float2 *d_rot = nullptr, *d_qlast = nullptr, *d_ckpt = nullptr;
-  float2* d_state[3] = {nullptr, nullptr, nullptr};   // boundary history, rotating by block (the deep kernel of block k still reads
-                                                      // state[k % 3] while the main kernel of block k+1 writes state[(k+2) % 3])
-  unsigned char* d_vfo_D = nullptr;                   // [vfo_pitch] half-band stages per column
+  float2* d_state[2] = {nullptr, nullptr};
   float2* d_xd = nullptr;       // all stage-D rows, per VFO: [hist][n_stage]
   float2** d_xd_rows = nullptr; // [vfo_pitch] pointer to stage-D index 0 of each column's row
   int* d_nco_len = nullptr;     // [vfo_pitch]
-  int* d_post_ctr = nullptr;    // work-item counters of the persistent post-processing kernels: [0] tail, [1 + g] deep kernel of group g
-  int post_ctas_deep = 0, post_ctas_tail = 0;   // their grid sizes
   int* d_err = nullptr;         // chained-CTA watchdog flag: device view of h_err (zero-copy pinned host memory)
   volatile int* h_err = nullptr;
   int nck_max = 0;
@@ -147,17 +117,12 @@ struct aeroddc_bank {
   unsigned char* d_in[2] = {nullptr, nullptr};
   size_t in_bytes = 0;
   size_t dev_bytes = 0;
-  size_t xd_total = 0;
 
   // host memory
   unsigned char* h_in[2] = {nullptr, nullptr};
   unsigned char* h_out[3] = {nullptr, nullptr, nullptr};   // three slots: a payload stays valid until the next wait()
 
-  // s_compute: main kernels. s_post: deep + tail + history shift of block k, overlapping the main kernel of block k+1
-  // (== s_compute for nested banks). s_dcc: DC removal one block ahead. s_copy: H2D of raw blocks. s_d2h: payloads out.
-  cudaStream_t s_compute = nullptr, s_post = nullptr, s_dcc = nullptr, s_copy = nullptr, s_d2h = nullptr;
-  cudaEvent_t ev_main[2] = {};   // main kernels of parity p finished
-  cudaEvent_t ev_dcc[2] = {};    // corrected block of parity p ready
+  cudaStream_t s_compute = nullptr, s_copy = nullptr, s_d2h = nullptr;   // kernels | H2D of raw blocks | D2H of payloads
   cudaEvent_t ev_tail[2] = {};   // payload rows of parity p written
   cudaEvent_t ev_d2h[2] = {};    // payload rows of parity p copied out (may be overwritten)
   cudaEvent_t ev_h2d[2] = {};
@@ -179,6 +144,8 @@ namespace {
 template <int NF, int FMT, bool FAST>
 cudaError_t launch_main_m(const MainParams& p, dim3 grid, cudaStream_t s) {
   const int smem = TileSmem<FMT>::kTotal;
+  cudaError_t e = cudaFuncSetAttribute(ddc_main_kernel<NF, FMT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
   ddc_main_kernel<NF, FMT, FAST><<<grid, kThreads, smem, s>>>(p);
   return cudaGetLastError();
 }
@@ -205,159 +172,102 @@ cudaError_t launch_main(int fmt, int nf, const MainParams& p, dim3 grid, cudaStr
 
 void free_all(aeroddc_bank* b) {
   cudaSetDevice(b->device);
-  cudaDeviceSynchronize();
-  cudaFree(b->d_post_ctr);
-  cudaFree(b->d_rot); cudaFree(b->d_qlast); cudaFree(b->d_ckpt); cudaFree(b->d_vfo_D);
-  for (int i = 0; i < 3; ++i) cudaFree(b->d_state[i]);
-  for (Group& g : b->groups) { cudaFree(g.d_sched); cudaFree(g.d_hand); cudaFree(g.d_mid[0]); cudaFree(g.d_mid[1]); }
+  if (b->s_compute) cudaStreamSynchronize(b->s_compute);
+  if (b->s_copy) cudaStreamSynchronize(b->s_copy);
+  if (b->s_d2h) cudaStreamSynchronize(b->s_d2h);
+  cudaFree(b->d_rot); cudaFree(b->d_qlast); cudaFree(b->d_ckpt);
+  cudaFree(b->d_state[0]); cudaFree(b->d_state[1]);
+  for (Group& g : b->groups) { cudaFree(g.d_flags); cudaFree(g.d_hand); }
   if (b->h_err) cudaFreeHost((void*)b->h_err);
-  cudaFree(b->d_dcc_out[0]); cudaFree(b->d_dcc_out[1]); cudaFree(b->d_dcc_state);
+  cudaFree(b->d_dcc_out); cudaFree(b->d_dcc_state);
   cudaFree(b->d_xd); cudaFree(b->d_xd_rows); cudaFree(b->d_nco_len); cudaFree(b->d_taps); cudaFree(b->d_hil_idx); cudaFree(b->d_tail); cudaFree(b->d_out);
   cudaFree(b->d_in[0]); cudaFree(b->d_in[1]);
   for (int i = 0; i < 2; ++i) {
     if (b->h_in[i]) cudaFreeHost(b->h_in[i]);
-    for (cudaEvent_t e : {b->ev_h2d[i], b->ev_tail[i], b->ev_d2h[i], b->ev_main[i], b->ev_dcc[i]}) if (e) cudaEventDestroy(e);
+    if (b->ev_h2d[i]) cudaEventDestroy(b->ev_h2d[i]);
   }
   for (int i = 0; i < 3; ++i) {
     if (b->h_out[i]) cudaFreeHost(b->h_out[i]);
-    for (cudaEvent_t e : {b->ev_done[i], b->ev_k0[i], b->ev_k1[i], b->ev_m0[i], b->ev_m1[i]}) if (e) cudaEventDestroy(e);
+    if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]);
+    if (b->ev_k0[i]) cudaEventDestroy(b->ev_k0[i]);
+    if (b->ev_k1[i]) cudaEventDestroy(b->ev_k1[i]);
+    if (b->ev_m0[i]) cudaEventDestroy(b->ev_m0[i]);
+    if (b->ev_m1[i]) cudaEventDestroy(b->ev_m1[i]);
   }
   if (b->ev_sw0) cudaEventDestroy(b->ev_sw0);
   if (b->ev_sw1) cudaEventDestroy(b->ev_sw1);
-  if (b->s_post && b->s_post != b->s_compute) cudaStreamDestroy(b->s_post);
-  for (cudaStream_t st : {b->s_compute, b->s_dcc, b->s_copy, b->s_d2h}) if (st) cudaStreamDestroy(st);
+  if (b->s_compute) cudaStreamDestroy(b->s_compute);
+  if (b->s_copy) cudaStreamDestroy(b->s_copy);
+  if (b->s_d2h) cudaStreamDestroy(b->s_d2h);
+  for (int i = 0; i < 2; ++i) { if (b->ev_tail[i]) cudaEventDestroy(b->ev_tail[i]); if (b->ev_d2h[i]) cudaEventDestroy(b->ev_d2h[i]); }
 }
 
-// Enqueue everything that follows the arrival of the raw block in device memory. The caller has already made the
-// first stream of the chain (s_dcc with DC correction, else s_compute) wait for the block.
-//   s_compute : [memset flags, main kernel] per group                       -> ev_main
-//   s_post    : deep kernel per group, tail, history shift (after ev_main)  -> ev_tail     (block k's post-processing
-//               overlaps the main kernel of block k+1; a nested bank runs both on one stream, group by group)
-//   s_d2h     : payload copy-out (after ev_tail)                            -> ev_done
-int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
-  const long long k = b->blocks_submitted;
-  const int slot = (int)(k % 3);   // payload/event slot
-  const int par = (int)(k & 1);
-  cudaStream_t sA = b->s_compute, sB = b->s_post;
-  const bool fast = b->mode == AERODDC_MODE_FAST;
+// enqueue everything that follows the arrival of the raw block in device memory
+int enqueue_block(aeroddc_bank* b, const void* dev_iq) {
+  const int slot = (int)(b->blocks_submitted % 3);   // payload/event slot
+  cudaStream_t s = b->s_compute;
+  const int par = (int)(b->blocks_submitted & 1);
   int launches = 0;
-  RawBlock raw = raw_in;
-  int raw_fmt = b->fmt;
-  if (b->dcc) {
-    // Sequential DC removal of the raw stream, one block ahead of the VFOs, which then read the corrected cf32 block.
-    // The recurrence is one dependent FMUL + FADD per sample; next to 16 warps that saturate the FP32 pipe its single
-    // warp would be starved (measured: 19x slower), so the CTA asks for a whole SM's shared memory and thereby keeps
-    // the SM to itself: 1/148 of the machine for the rate-limiting step of a DC-corrected stream.
-    const size_t ex = b->dcc_smem;
-    if (b->fmt == AERODDC_CU8) dcc_kernel<0><<<1, 32, ex, b->s_dcc>>>(raw, b->d_dcc_out[par], b->d_dcc_state, b->B);
-    else if (b->fmt == AERODDC_CS16) dcc_kernel<1><<<1, 32, ex, b->s_dcc>>>(raw, b->d_dcc_out[par], b->d_dcc_state, b->B);
-    else dcc_kernel<2><<<1, 32, ex, b->s_dcc>>>(raw, b->d_dcc_out[par], b->d_dcc_state, b->B);
+  CU(cudaEventRecord(b->ev_k0[slot], s));
+  if (b->dcc) {   // sequential DC removal of the raw stream; the VFOs then read the corrected cf32 block
+    if (b->fmt == AERODDC_CU8) dcc_kernel<0><<<1, 32, 0, s>>>(dev_iq, b->d_dcc_out, b->d_dcc_state, b->B);
+    else if (b->fmt == AERODDC_CS16) dcc_kernel<1><<<1, 32, 0, s>>>(dev_iq, b->d_dcc_out, b->d_dcc_state, b->B);
+    else dcc_kernel<2><<<1, 32, 0, s>>>(dev_iq, b->d_dcc_out, b->d_dcc_state, b->B);
     CU(cudaGetLastError());
     ++launches;
-    CU(cudaEventRecord(b->ev_dcc[par], b->s_dcc));
-    CU(cudaStreamWaitEvent(sA, b->ev_dcc[par], 0));
-    raw.slice[0] = b->d_dcc_out[par];
-    raw.n_slices = 1;
-    raw.slice_len = b->B;
-    raw_fmt = AERODDC_CF32;
+    dev_iq = b->d_dcc_out;
   }
-  CU(cudaEventRecord(b->ev_k0[slot], sA));
-  if (b->nested) CU(cudaMemsetAsync(b->d_post_ctr, 0, sizeof(int) * (1 + b->groups.size()), sA));
-  CU(cudaEventRecord(b->ev_m0[slot], sA));
-  const float2* state_in = b->d_state[k % 3];
-  float2* state_out = b->d_state[(k + 1) % 3];
-
-  auto launch_deep = [&](const Group& g, cudaStream_t st) -> int {
-    DeepParams d;
-    d.mid = g.d_mid[par];
-    d.state_in = state_in;
-    d.state_out = state_out;
-    d.xd_rows = b->d_xd_rows;
-    d.vfo_D = b->d_vfo_D;
-    d.counter = b->d_post_ctr + 1 + (&g - &b->groups[0]);
-    d.vfo_pitch = b->vfo_pitch;
-    d.vfo_base = g.base;
-    d.vfo_count = g.count;
-    d.DA = g.DA;
-    d.n_mid = g.n_mid;
-    d.T = g.deep_T;
-    d.Wd = kDeepWarm;
-    d.nranges = g.deep_ranges;
-    d.ngroups = (g.count + 31) / 32;
-    d.one = 1.0f;
-    const int items = d.nranges * d.ngroups;
-    const unsigned grid = (unsigned)std::min(items, b->post_ctas_deep);
-    const size_t ring = sizeof(float2) * 2 * kDeepStep * 32;
-    if (fast) ddc_deep_kernel<true><<<grid, 32, ring, st>>>(d);
-    else ddc_deep_kernel<false><<<grid, 32, ring, st>>>(d);
-    CU(cudaGetLastError());
-    ++launches;
-    return AERODDC_OK;
-  };
-
+  CU(cudaEventRecord(b->ev_m0[slot], s));
   for (const Group& g : b->groups) {
     MainParams p;
-    if (g.parent < 0) {
-      p.raw = raw;
-    } else {   // a sub-VFO group reads its parent's stage-D stream of this block (already enqueued on this stream)
-      p.raw.slice[0] = b->d_xd + b->vfos[g.parent].xd_off + b->vfos[g.parent].hist;
-      p.raw.n_slices = 1;
-      p.raw.slice_len = g.blk_in;
-    }
+    // a sub-VFO group reads its parent's stage-D stream of this block (already enqueued on this stream)
+    p.iq = g.parent < 0 ? dev_iq : (const void*)(b->d_xd + b->vfos[g.parent].xd_off + b->vfos[g.parent].hist);
     p.ckpt = b->d_ckpt;
     p.rot = b->d_rot;
     p.qlast = b->d_qlast;
-    p.state_in = state_in;
-    p.state_out = state_out;
-    p.mid = g.direct ? nullptr : g.d_mid[par];
-    p.n_mid = g.n_mid;
+    p.state_in = b->d_state[par];
+    p.state_out = b->d_state[par ^ 1];
     p.xd_rows = b->d_xd_rows;
-    p.block_abs = k * (long long)g.blk_in;
+    p.block_abs = b->blocks_submitted * (long long)g.blk_in;
     p.vfo_pitch = b->vfo_pitch;
     p.vfo_base = g.base;
     p.vfo_count = g.count;
-    p.DA = g.DA;
+    p.D = g.D;
     p.B = g.blk_in;
     p.S = g.S;
     p.W = g.W;
     p.nseg = g.nseg;
+    p.Wb = g.Wb;
     p.nco_len = g.fs_in;
     p.one = 1.0f;
     p.transient = 4 * kNcoStride;
     p.nck = b->nck_max;
+    p.Q = g.Q;
     p.P = g.P;
     p.ngroups = (g.count + kVfoPerCta - 1) / kVfoPerCta;
-    p.nchains = g.nchains;
-    p.sched = g.d_sched;
+    p.flags = g.d_flags;
+    p.ticket = g.d_flags + (size_t)p.ngroups * g.nseg;   // the counter lives behind the flags
     p.hand = g.d_hand;
     p.err = b->d_err;
-    CU(cudaMemsetAsync(g.d_sched, 0, sizeof(int) * g.sched_words, sA));
-    dim3 grid((unsigned)(p.ngroups + g.nparts));
-    CU(launch_main(g.parent < 0 ? raw_fmt : AERODDC_CF32, g.DA, p, grid, sA, fast));
+    CU(cudaMemsetAsync(g.d_flags, 0, sizeof(int) * ((size_t)p.ngroups * g.nseg + 1), s));
+    dim3 grid((unsigned)(p.ngroups * (1 + g.Q * g.nseg)));
+    CU(launch_main((g.parent < 0 && !b->dcc) ? b->fmt : AERODDC_CF32, std::min(g.D, kFastStages), p, grid, s, b->mode == AERODDC_MODE_FAST));
     ++launches;
-    if (b->nested && !g.direct) { const int rc = launch_deep(g, sA); if (rc != AERODDC_OK) return rc; }
   }
-  CU(cudaEventRecord(b->ev_m1[slot], sA));
-  if (!b->nested) {
-    CU(cudaEventRecord(b->ev_main[par], sA));
-    CU(cudaStreamWaitEvent(sB, b->ev_main[par], 0));
-    CU(cudaMemsetAsync(b->d_post_ctr, 0, sizeof(int) * (1 + b->groups.size()), sB));
-    for (const Group& g : b->groups) { const int rc = launch_deep(g, sB); if (rc != AERODDC_OK) return rc; }
-  }
+  CU(cudaEventRecord(b->ev_m1[slot], s));
   {
     // payload rows are double-buffered by block parity; wait until the copy-out of this parity (two blocks ago) is done
-    if (k >= 2) CU(cudaStreamWaitEvent(sB, b->ev_d2h[par], 0));
-    const int items = b->tail_chunks * (int)b->vfos.size();
-    tail_kernel<<<(unsigned)std::min(items, b->post_ctas_tail), kTailThreads, b->tail_smem, sB>>>(
-        b->d_tail, 1.0f, (size_t)par * b->out_total, b->d_post_ctr, (int)b->vfos.size(), b->tail_chunks);
+    if (b->blocks_submitted >= 2) CU(cudaStreamWaitEvent(s, b->ev_d2h[par], 0));
+    dim3 grid(b->tail_chunks, (unsigned)b->vfos.size());
+    tail_kernel<<<grid, kTailThreads, b->tail_smem, s>>>(b->d_tail, 1.0f, (size_t)par * b->out_total);
     CU(cudaGetLastError());
     ++launches;
   }
-  CU(cudaEventRecord(b->ev_k1[slot], sB));
-  CU(cudaEventRecord(b->ev_tail[par], sB));
+  CU(cudaEventRecord(b->ev_k1[slot], s));
+  CU(cudaEventRecord(b->ev_tail[par], s));
   // keep the last `hist` stage-D samples of every VFO in front of the next block
   if (b->any_hist) {
-    xd_shift_kernel<<<(unsigned)b->vfos.size(), 256, 0, sB>>>(b->d_tail);
+    xd_shift_kernel<<<(unsigned)b->vfos.size(), 256, 0, s>>>(b->d_tail);
     CU(cudaGetLastError());
     ++launches;
   }
@@ -368,15 +278,6 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
   CU(cudaEventRecord(b->ev_done[slot], b->s_d2h));
   b->launches_per_block = launches;
   b->blocks_submitted++;
-  return AERODDC_OK;
-}
-
-int check_submit(aeroddc_bank* b, size_t n_complex) {
-  if (!b->finalized) return fail(AERODDC_ERR_STATE, "bank not finalized");
-  if (b->poisoned) return fail(AERODDC_ERR_CUDA, "the bank stopped after an internal error (a chained segment CTA timed out); destroy it");
-  if (n_complex != (size_t)b->B)
-    return fail(AERODDC_ERR_ARG, "block of %zu samples, bank was created for %d (vfo.cpp:155,164 block contract)", n_complex, b->B);
-  if (b->blocks_submitted - b->blocks_done >= 2) return fail(AERODDC_ERR_STATE, "two blocks already in flight; call wait()");
   return AERODDC_OK;
 }
 
@@ -431,34 +332,31 @@ int aeroddc_bank_create(aeroddc_bank** out, int sample_rate, int block_len, int 
 int aeroddc_plan_segments(int block_len, int decim_count, int n_vfos, int n_sm, double waves, int parts, aeroddc_segment_plan* out) {
   if (!out || block_len <= 0 || decim_count < 0 || decim_count > kMaxStages || n_vfos < 1 || n_sm < 1 || !(waves > 0))
     return fail(AERODDC_ERR_ARG, "bad planning arguments");
-  const int DA = std::min(decim_count, kFastStages);   // stages of the main kernel; the deep kernel needs no segmentation plan
-  const int cstep = ilcm(kChunk, 1 << DA);
+  const int D = decim_count;
+  const int cstep = ilcm(kChunk, 1 << D);
   if (block_len % cstep) return fail(AERODDC_ERR_ARG, "block of %d samples is not a multiple of %d", block_len, cstep);
-  const int align = ilcm(kNcoStride, 1 << DA);
-  out->warmup = DA == 0 ? 0 : ((10 << DA) + cstep - 1) / cstep * cstep;     // 10*(2^DA - 1) samples reach the last register stage's history
-  out->boundary_warmup = decim_count == 0 ? 0 : (11 << decim_count);        // the next block's shifted history needs 11 samples per stage
+  const int align = ilcm(kNcoStride, 1 << D);
+  out->warmup = D == 0 ? 0 : ((10 << D) + cstep - 1) / cstep * cstep;   // 10*(2^D - 1) samples reach the deepest stage's history
+  out->boundary_warmup = D == 0 ? 0 : (11 << D);                        // the next block's shifted history needs 11 samples per stage
   const int groups = (n_vfos + kVfoPerCta - 1) / kVfoPerCta;
-  // One wave of one-warp CTAs (kCtasPerSm per SM), plus a few percent, cuts the block into segments, each paying one
-  // warm-up of W samples. The warp scheduler favours some resident warps, so equal CTAs of a single wave would finish
-  // at different times; each segment is therefore a chain of Q parts handed from CTA to CTA through HBM, and the
-  // kernel's FIFO of ready chains (a few more chains than SM slots keep it non-empty) lets every chain advance at the
-  // average pace of all slots.
-  const int target = std::max(1, (int)std::ceil((double)kCtasPerSm * n_sm * waves * 1.04 / groups));
+  // One wave of CTAs (kCtasPerSm per SM) cuts the block into segments, each paying one warm-up of W samples.
+  // The warp scheduler favours some resident warps, so equal CTAs of a single wave finish at different times;
+  // each segment is therefore processed as Q chained parts by Q short CTAs (state handed over through HBM),
+  // which evens the load without further warm-ups.
+  const int target = std::max(1, (int)std::floor((double)kCtasPerSm * n_sm * waves / groups) - 1);   // -1: the boundary CTA
   int S = (block_len + target - 1) / target;
-  S = std::max(S, std::max(2 * out->warmup, 512));   // a small bank: short segments, for latency rather than efficiency
+  S = std::max(S, std::max(4 * out->warmup, 4096));
   S = (S + align - 1) / align * align;
   out->segment_len = S;
   out->n_segments = (block_len + S - 1) / S;
   int Q = parts > 0 ? parts : 16;
-  const int pal = ilcm(kTile, 1 << DA);
-  while (Q > 1 && S / Q < 8 * pal) --Q;   // keep parts long enough (2048 samples) that the hand-over stays negligible
+  const int pal = ilcm(kTile, 1 << D);
+  while (Q > 1 && S / Q < 8 * pal) --Q;   // keep parts long enough that the hand-over stays negligible
   Q = std::min(Q, 60);
   out->parts = Q;
   out->part_len = ((S + Q - 1) / Q + pal - 1) / pal * pal;
   out->vfo_groups = groups;
-  const int last = block_len - (out->n_segments - 1) * S;                      // the last segment may be shorter
-  const int parts_total = (out->n_segments - 1) * ((S + out->part_len - 1) / out->part_len) + (last + out->part_len - 1) / out->part_len;
-  out->ctas = groups * (1 + parts_total);
+  out->ctas = groups * (1 + Q * out->n_segments);
   return AERODDC_OK;
 }
 
@@ -529,64 +427,40 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
   if (prop.major < 10) return fail(AERODDC_ERR_CUDA, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
   b->n_sm = prop.multiProcessorCount;
 
-  // ---- group VFOs by (input stream, min(D, 5)); raw-fed groups first so that parents run before children ----
+  // ---- group VFOs by (input stream, D); raw-fed groups first so that parents run before children ----
   const int nv = (int)b->vfos.size();
   int col = 0;
   for (int parent = -1; parent < nv; ++parent) {
     if (parent >= 0 && b->vfos[parent].children == 0) continue;
-    if (parent >= 0) b->nested = true;
-    for (int DA = 0; DA <= kFastStages; ++DA) {
+    for (int D = 0; D <= kMaxStages; ++D) {
       Group g;
-      g.parent = parent; g.DA = DA; g.Dmax = 0; g.base = col; g.count = 0;
+      g.parent = parent; g.D = D; g.base = col; g.count = 0;
       for (int i = 0; i < nv; ++i)
-        if (b->vfos[i].d.parent == parent && std::min(b->vfos[i].d.decim_count, kFastStages) == DA) {
+        if (b->vfos[i].d.parent == parent && b->vfos[i].d.decim_count == D) {
           b->vfos[i].slot = col++; g.count++;
-          g.Dmax = std::max(g.Dmax, b->vfos[i].d.decim_count);
           g.fs_in = b->vfos[i].fs_in; g.blk_in = b->vfos[i].blk_in;
         }
       if (g.count) b->groups.push_back(g);
     }
   }
   b->vfo_pitch = (col + 3) & ~3;
-  for (const Group& g : b->groups) if (g.Dmax <= kFastStages) b->nested = true;   // such a group writes its stage-D rows directly: keep order
   const char* env_waves = getenv("AERODDC_WAVES");
   const double waves = env_waves ? std::max(0.05, atof(env_waves)) : 1.0;
   const char* env_parts = getenv("AERODDC_PARTS");
   const int env_parts_n = env_parts ? std::max(1, atoi(env_parts)) : 0;
-  size_t bytes = 0;
-  auto dmalloc = [&](void** p, size_t n) { bytes += n; return cudaMalloc(p, n); };
   for (Group& g : b->groups) {
     aeroddc_segment_plan pl;
-    const int rc = aeroddc_plan_segments(g.blk_in, g.DA, g.count, b->n_sm, waves, env_parts_n, &pl);
+    const int rc = aeroddc_plan_segments(g.blk_in, g.D, g.count, b->n_sm, waves, env_parts_n, &pl);
     if (rc != AERODDC_OK) return rc;
-    g.W = pl.warmup; g.S = pl.segment_len; g.nseg = pl.n_segments; g.Q = pl.parts; g.P = pl.part_len;
-    g.direct = g.Dmax <= kFastStages;
-    g.mid_pitch = 32 * ((g.count + 31) / 32);   // whole 32-VFO groups: [group][time][32 lanes]
-    g.n_mid = g.blk_in >> g.DA;
-    // time ranges of the deep kernel: long where the stream is long (each range re-reads 72 samples of run-in), short
-    // where a small bank would otherwise leave the machine idle
-    g.deep_T = g.n_mid >= 65536 ? 1024 : (g.n_mid >= 8192 ? 256 : 64);   // multiples of the deep kernel's 32-sample step
-    g.deep_ranges = (g.n_mid + g.deep_T - 1) / g.deep_T;
-    const int ng = (g.count + kVfoPerCta - 1) / kVfoPerCta;
-    g.nchains = ng * g.nseg;
-    g.nparts = pl.ctas - ng;
-    g.sched_words = 2 + (size_t)g.nparts;   // counters + parts done per chain + queue (one entry per part after a chain's first)
-    CU(dmalloc((void**)&g.d_sched, sizeof(int) * g.sched_words));
-    CU(cudaMemset(g.d_sched, 0, sizeof(int) * g.sched_words));
-    CU(dmalloc((void**)&g.d_hand, sizeof(float2) * (size_t)g.nchains * kHandSlots * kThreads));
-    if (!g.direct)
-      for (int i = 0; i < 2; ++i) CU(dmalloc((void**)&g.d_mid[i], sizeof(float2) * (size_t)g.n_mid * g.mid_pitch));
+    g.W = pl.warmup; g.Wb = pl.boundary_warmup; g.S = pl.segment_len; g.nseg = pl.n_segments; g.Q = pl.parts; g.P = pl.part_len;
   }
-  CU(dmalloc((void**)&b->d_post_ctr, sizeof(int) * (1 + b->groups.size())));
-  // Persistent grids of the post-processing kernels, in CTAs per SM. A flat bank overlaps block k's post-processing with
-  // block k+1's main kernel; measured on B200, a few light warps per SM beside the FP32-saturating main kernel are starved
-  // by the warp scheduler (2 + 1 CTAs per SM: the deep kernel then takes longer than the main kernel, 25 ms per step instead
-  // of 21), so both kernels take whole SMs' worth of slots for a short time instead.
-  const char* env_post = getenv("AERODDC_POST_CTAS");   // experiments: "deep,tail" CTAs per SM
-  int per_sm_deep = kDeepCtasPerSm, per_sm_tail = 6;
-  if (env_post) sscanf(env_post, "%d,%d", &per_sm_deep, &per_sm_tail);
-  b->post_ctas_deep = std::max(1, per_sm_deep) * b->n_sm;
-  b->post_ctas_tail = std::max(1, per_sm_tail) * b->n_sm;
+
+  for (Group& g : b->groups) {
+    const size_t nk = (size_t)((g.count + kVfoPerCta - 1) / kVfoPerCta) * g.nseg;
+    CU(cudaMalloc((void**)&g.d_flags, sizeof(int) * (nk + 1)));   // + the ticket counter
+    CU(cudaMemset(g.d_flags, 0, sizeof(int) * (nk + 1)));
+    CU(cudaMalloc((void**)&g.d_hand, sizeof(float2) * nk * kHandSlots * kThreads));
+  }
   CU(cudaHostAlloc((void**)&b->h_err, sizeof(int), cudaHostAllocMapped));
   *b->h_err = 0;
   CU(cudaHostGetDevicePointer((void**)&b->d_err, (void*)b->h_err, 0));
@@ -594,25 +468,23 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
   // ---- constant tables ----
   std::vector<float2> h_rot(b->vfo_pitch, make_float2(1.0f, 0.0f));
   std::vector<int> h_len(b->vfo_pitch, 1);
-  std::vector<unsigned char> h_D(b->vfo_pitch, 0);
   b->nck_max = 1;
   for (const VfoRec& r : b->vfos) {
     design_rotation((double)r.fs_in, r.d.mixer_freq, &h_rot[r.slot].x, &h_rot[r.slot].y);
     h_len[r.slot] = r.fs_in;
-    h_D[r.slot] = (unsigned char)r.d.decim_count;
     b->nck_max = std::max(b->nck_max, (r.fs_in + kNcoStride - 1) / kNcoStride);
   }
+  size_t bytes = 0;
+  auto dmalloc = [&](void** p, size_t n) { bytes += n; return cudaMalloc(p, n); };
   CU(dmalloc((void**)&b->d_rot, sizeof(float2) * b->vfo_pitch));
   CU(dmalloc((void**)&b->d_qlast, sizeof(float2) * b->vfo_pitch));
   CU(dmalloc((void**)&b->d_nco_len, sizeof(int) * b->vfo_pitch));
-  CU(dmalloc((void**)&b->d_vfo_D, b->vfo_pitch));
   CU(dmalloc((void**)&b->d_ckpt, sizeof(float2) * (size_t)b->nck_max * b->vfo_pitch));
   CU(cudaMemset(b->d_ckpt, 0, sizeof(float2) * (size_t)b->nck_max * b->vfo_pitch));
   CU(cudaMemset(b->d_qlast, 0, sizeof(float2) * b->vfo_pitch));
   CU(cudaMemcpy(b->d_rot, h_rot.data(), sizeof(float2) * b->vfo_pitch, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(b->d_nco_len, h_len.data(), sizeof(int) * b->vfo_pitch, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(b->d_vfo_D, h_D.data(), b->vfo_pitch, cudaMemcpyHostToDevice));
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 2; ++i) {
     const size_t n = sizeof(float2) * (size_t)kMaxStages * kStateSlots * b->vfo_pitch;
     CU(dmalloc((void**)&b->d_state[i], n));
     CU(cudaMemset(b->d_state[i], 0, n));   // first block: all-zero history (dsp.cpp:48-52)
@@ -636,7 +508,6 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
     out_off += (r.out_bytes + 15) & ~(size_t)15;
   }
   b->out_total = std::max<size_t>(out_off, 16);
-  b->xd_total = xd_total;
   CU(dmalloc((void**)&b->d_xd, sizeof(float2) * xd_total));
   CU(cudaMemset(b->d_xd, 0, sizeof(float2) * xd_total));
   std::vector<float2*> h_rows(b->vfo_pitch, b->d_xd);
@@ -690,16 +561,12 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
   }
   b->tail_smem = tail_smem;
   b->tail_chunks = std::max(1, (max_out + kTailChunk - 1) / kTailChunk);
-  CU(raise_tail_smem_limit(b->device, tail_smem));
+  CU(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
   CU(dmalloc((void**)&b->d_tail, sizeof(TailVfo) * nv));
   CU(cudaMemcpy(b->d_tail, h_tail.data(), sizeof(TailVfo) * nv, cudaMemcpyHostToDevice));
 
   if (b->dcc) {
-    b->dcc_smem = (size_t)prop.sharedMemPerBlockOptin;   // everything an SM can give one CTA: no other CTA fits beside it
-    CU(cudaFuncSetAttribute(dcc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->dcc_smem));
-    CU(cudaFuncSetAttribute(dcc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->dcc_smem));
-    CU(cudaFuncSetAttribute(dcc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->dcc_smem));
-    for (int i = 0; i < 2; ++i) CU(dmalloc((void**)&b->d_dcc_out[i], sizeof(float) * 2 * (size_t)b->B));
+    CU(dmalloc((void**)&b->d_dcc_out, sizeof(float) * 2 * (size_t)b->B));
     CU(dmalloc((void**)&b->d_dcc_state, sizeof(float) * 2));
     CU(cudaMemset(b->d_dcc_state, 0, sizeof(float) * 2));
   }
@@ -720,25 +587,13 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
   }
   CU(cudaEventCreate(&b->ev_sw0));
   CU(cudaEventCreate(&b->ev_sw1));
-  // the post-processing stream outranks the main stream: its small kernels take the next SM slots that come free while
-  // the following block's main kernel is running
-  int prio_lo = 0, prio_hi = 0;
-  CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-  CU(cudaStreamCreateWithPriority(&b->s_compute, cudaStreamNonBlocking, prio_lo));
-  if (b->nested) b->s_post = b->s_compute;
-  else CU(cudaStreamCreateWithPriority(&b->s_post, cudaStreamNonBlocking, prio_hi));
-  CU(cudaStreamCreateWithPriority(&b->s_dcc, cudaStreamNonBlocking, prio_hi));
+  CU(cudaStreamCreateWithFlags(&b->s_compute, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&b->s_copy, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&b->s_d2h, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
     CU(cudaEventCreateWithFlags(&b->ev_tail[i], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&b->ev_d2h[i], cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&b->ev_main[i], cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&b->ev_dcc[i], cudaEventDisableTiming));
   }
-  // every instance of the main kernel may be launched by this bank: raise their dynamic shared-memory limits once
-  // (the values are compile-time constants, so banks never disagree about them)
-  // (all are below the 48 KB default; nothing to do)
 
   // ---- NCO checkpoints: the exact sequential recurrence, one thread per VFO ----
   {
@@ -753,42 +608,24 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
   return AERODDC_OK;
 }
 
-int aeroddc_bank_submit_device_sliced(aeroddc_bank* b, const void* const* slices, int n_slices, size_t slice_len, size_t n_complex,
-                                      void* const* ready_events, int n_events) {
-  if (!b || !slices) return fail(AERODDC_ERR_ARG, "NULL argument");
-  int rc = check_submit(b, n_complex);
-  if (rc != AERODDC_OK) return rc;
-  if (n_slices < 1 || n_slices > kMaxSlices) return fail(AERODDC_ERR_ARG, "n_slices must be 1..%d", kMaxSlices);
-  if (n_slices > 1 && (slice_len < (size_t)kTile || slice_len % kChunk))
-    return fail(AERODDC_ERR_ARG, "slice_len must be a multiple of %d and at least %d complex samples", kChunk, kTile);
-  if (n_slices > 1 && (slice_len * (size_t)(n_slices - 1) >= n_complex || slice_len * (size_t)n_slices < n_complex))
-    return fail(AERODDC_ERR_ARG, "%d slices of %zu samples do not tile a block of %zu", n_slices, slice_len, n_complex);
-  if (n_events < 0 || (n_events > 0 && !ready_events)) return fail(AERODDC_ERR_ARG, "bad ready_events");
-  RawBlock raw;
-  for (int i = 0; i < kMaxSlices; ++i) raw.slice[i] = nullptr;
-  for (int i = 0; i < n_slices; ++i) {
-    if (!slices[i]) return fail(AERODDC_ERR_ARG, "slice %d is NULL", i);
-    if ((uintptr_t)slices[i] & 15) return fail(AERODDC_ERR_ARG, "device block must be 16-byte aligned");
-    raw.slice[i] = slices[i];
-  }
-  raw.n_slices = n_slices;
-  raw.slice_len = n_slices > 1 ? (int)slice_len : b->B;
-  CU(cudaSetDevice(b->device));
-  cudaStream_t first = b->dcc ? b->s_dcc : b->s_compute;
-  for (int i = 0; i < n_events; ++i)
-    if (ready_events[i]) CU(cudaStreamWaitEvent(first, (cudaEvent_t)ready_events[i], 0));
-  return enqueue_block(b, raw);
-}
-
 int aeroddc_bank_submit_device(aeroddc_bank* b, const void* dev_iq, size_t n_complex, void* ready_event) {
   if (!b || !dev_iq) return fail(AERODDC_ERR_ARG, "NULL argument");
-  return aeroddc_bank_submit_device_sliced(b, &dev_iq, 1, n_complex, n_complex, &ready_event, ready_event ? 1 : 0);
+  if (!b->finalized) return fail(AERODDC_ERR_STATE, "bank not finalized");
+  if (n_complex != (size_t)b->B)
+    return fail(AERODDC_ERR_ARG, "block of %zu samples, bank was created for %d (vfo.cpp:155,164 block contract)", n_complex, b->B);
+  if (b->blocks_submitted - b->blocks_done >= 2) return fail(AERODDC_ERR_STATE, "two blocks already in flight; call wait()");
+  if ((uintptr_t)dev_iq & 15) return fail(AERODDC_ERR_ARG, "device block must be 16-byte aligned");
+  CU(cudaSetDevice(b->device));
+  if (ready_event) CU(cudaStreamWaitEvent(b->s_compute, (cudaEvent_t)ready_event, 0));
+  return enqueue_block(b, dev_iq);
 }
 
 int aeroddc_bank_submit(aeroddc_bank* b, const void* host_iq, size_t n_complex) {
   if (!b || !host_iq) return fail(AERODDC_ERR_ARG, "NULL argument");
-  int rc = check_submit(b, n_complex);
-  if (rc != AERODDC_OK) return rc;
+  if (!b->finalized) return fail(AERODDC_ERR_STATE, "bank not finalized");
+  if (n_complex != (size_t)b->B)
+    return fail(AERODDC_ERR_ARG, "block of %zu samples, bank was created for %d (vfo.cpp:155,164 block contract)", n_complex, b->B);
+  if (b->blocks_submitted - b->blocks_done >= 2) return fail(AERODDC_ERR_STATE, "two blocks already in flight; call wait()");
   CU(cudaSetDevice(b->device));
   const int slot = (int)(b->blocks_submitted & 1);
   const void* src = host_iq;
@@ -799,13 +636,8 @@ int aeroddc_bank_submit(aeroddc_bank* b, const void* host_iq, size_t n_complex) 
   // d_in[slot] was last read by the block submitted two calls ago, which wait() has retired
   CU(cudaMemcpyAsync(b->d_in[slot], src, b->in_bytes, cudaMemcpyHostToDevice, b->s_copy));
   CU(cudaEventRecord(b->ev_h2d[slot], b->s_copy));
-  CU(cudaStreamWaitEvent(b->dcc ? b->s_dcc : b->s_compute, b->ev_h2d[slot], 0));
-  RawBlock raw;
-  for (int i = 0; i < kMaxSlices; ++i) raw.slice[i] = nullptr;
-  raw.slice[0] = b->d_in[slot];
-  raw.n_slices = 1;
-  raw.slice_len = b->B;
-  return enqueue_block(b, raw);
+  CU(cudaStreamWaitEvent(b->s_compute, b->ev_h2d[slot], 0));
+  return enqueue_block(b, b->d_in[slot]);
 }
 
 int aeroddc_bank_wait(aeroddc_bank* b) {
@@ -814,18 +646,12 @@ int aeroddc_bank_wait(aeroddc_bank* b) {
   CU(cudaSetDevice(b->device));
   const int slot = (int)(b->blocks_done % 3);
   CU(cudaEventSynchronize(b->ev_done[slot]));
-  b->blocks_done++;
-  if (b->poisoned || *b->h_err) {
-    // A chained CTA gave up waiting for its predecessor (never observed; the watchdog exists so that a scheduling
-    // surprise cannot hang the GPU). Whatever that block produced is garbage: wipe it and stop the bank.
-    b->poisoned = true;
-    for (int i = 0; i < 3; ++i) memset(b->h_out[i], 0, b->out_total);
-    return fail(AERODDC_ERR_CUDA, "a chained segment CTA timed out waiting for its predecessor (internal error); payloads were zeroed, the bank is stopped");
-  }
   CU(cudaEventElapsedTime(&b->last_kernel_ms, b->ev_k0[slot], b->ev_k1[slot]));
   CU(cudaEventElapsedTime(&b->last_main_ms, b->ev_m0[slot], b->ev_m1[slot]));
   b->last_launches = b->launches_per_block;
   b->cur_out = slot;
+  b->blocks_done++;
+  if (*b->h_err) return fail(AERODDC_ERR_CUDA, "a chained segment CTA timed out waiting for its predecessor (internal error)");
   return AERODDC_OK;
 }
 
@@ -836,21 +662,6 @@ int aeroddc_bank_process(aeroddc_bank* b, const void* host_iq, size_t n_complex)
     rc = aeroddc_bank_wait(b);
     if (rc != AERODDC_OK) return rc;
   }
-  return AERODDC_OK;
-}
-
-int aeroddc_bank_reset(aeroddc_bank* b) {
-  if (!b) return fail(AERODDC_ERR_ARG, "NULL bank");
-  if (!b->finalized) return fail(AERODDC_ERR_STATE, "bank not finalized");
-  if (b->blocks_done != b->blocks_submitted) return fail(AERODDC_ERR_STATE, "blocks in flight; call wait() first");
-  CU(cudaSetDevice(b->device));
-  CU(cudaDeviceSynchronize());
-  for (int i = 0; i < 3; ++i) CU(cudaMemset(b->d_state[i], 0, sizeof(float2) * (size_t)kMaxStages * kStateSlots * b->vfo_pitch));
-  CU(cudaMemset(b->d_xd, 0, sizeof(float2) * b->xd_total));
-  if (b->d_dcc_state) CU(cudaMemset(b->d_dcc_state, 0, sizeof(float) * 2));
-  b->blocks_submitted = b->blocks_done = 0;
-  b->cur_out = -1;
-  if (b->poisoned) return fail(AERODDC_ERR_CUDA, "the bank stopped after an internal error; destroy it");
   return AERODDC_OK;
 }
 
@@ -888,7 +699,7 @@ int aeroddc_bank_stage_d(aeroddc_bank* b, int vfo, float* host_out, size_t cap_c
   const size_t n = std::min<size_t>(cap_complex, (size_t)r.plan.n_stage);
   // the block stays at [hist, hist + n_stage) of the row until the next block overwrites it; the
   // history shift only rewrites [0, hist)
-  CU(cudaStreamSynchronize(b->s_post));
+  CU(cudaStreamSynchronize(b->s_compute));
   CU(cudaMemcpy(host_out, b->d_xd + r.xd_off + r.hist, n * sizeof(float2), cudaMemcpyDeviceToHost));
   return (int)r.plan.n_stage;
 }

@@ -65,18 +65,17 @@ typedef struct aeroddc_vfo_desc {
  * buflen arithmetic of Publisher::loadSettings (publisher.cpp:93-100). */
 int aeroddc_bank_create(aeroddc_bank **out, int sample_rate, int block_len, int in_format, int device);
 
-/* How the bank cuts a block of one VFO group (VFOs sharing input stream and DA = min(D, 5), the half-band stages the
- * main kernel runs in registers; stages 5..D-1 run in the deep kernel at <= 1/32 of the rate and need no plan) into
- * work for the main kernel (pure host arithmetic, no device needed; exposed for inspection and tests). All lengths in
- * input samples. Invariants: segment_len and part_len are multiples of 256; n_segments*segment_len >= block_len;
- * parts*part_len >= segment_len; segment_len >= 2*warmup. */
+/* How the bank cuts a block of one VFO group (VFOs sharing input stream and D) into work for the main kernel
+ * (pure host arithmetic, no device needed; exposed for inspection and tests). All lengths in input samples.
+ * Invariants: segment_len and part_len are multiples of lcm(256, 2^D); n_segments*segment_len >= block_len;
+ * parts*part_len >= segment_len; segment_len >= 4*warmup. */
 typedef struct aeroddc_segment_plan {
-  int warmup;           /* W = 10*2^DA (rounded to the chunk): samples a segment re-processes to rebuild its history */
-  int boundary_warmup;  /* 11*2^D: samples the boundary CTA re-processes for the next block's shifted history      */
+  int warmup;           /* W = 10*2^D (rounded to the chunk): samples a segment re-processes to rebuild its history */
+  int boundary_warmup;  /* 11*2^D: samples the boundary CTA re-processes for the next block's shifted history     */
   int segment_len, n_segments;
-  int parts, part_len;  /* a full segment runs as `parts` chained CTAs of part_len samples (the last one may need fewer) */
-  int vfo_groups;       /* CTAs side by side: ceil(n_vfos / 32), one warp of 32 VFOs each                          */
-  int ctas;             /* grid size of the launch                                                                 */
+  int parts, part_len;  /* each segment runs as `parts` chained CTAs of part_len samples                          */
+  int vfo_groups;       /* CTAs side by side: ceil(n_vfos / 128)                                                  */
+  int ctas;             /* grid size of the launch                                                                */
 } aeroddc_segment_plan;
 int aeroddc_plan_segments(int block_len, int decim_count, int n_vfos, int n_sm, double waves, int parts, aeroddc_segment_plan *out);
 
@@ -118,12 +117,6 @@ int aeroddc_bank_process(aeroddc_bank *bank, const void *host_iq, size_t n_compl
 int aeroddc_bank_submit(aeroddc_bank *bank, const void *host_iq, size_t n_complex);
 int aeroddc_bank_wait(aeroddc_bank *bank);
 
-/* Rewind the bank to stream position 0: all filter history, the oscillator position, the stage-D history and the DC
- * average return to their freshly initialised values (as after vfo::init, vfo.cpp:57-139), the VFO set and every
- * design table stay. Nothing may be in flight. Used when a file source is re-opened and by bench.py's parity leg,
- * which replays six known blocks through the very bank object it has just timed. */
-int aeroddc_bank_reset(aeroddc_bank *bank);
-
 /* Pinned host staging ring ("pinned host ring plus async H2D", replaces the malloc'ed samplesBuf
  * of Publisher::readerThread, publisher.cpp:238,267-268): slot 0/1, each block_len samples. A
  * source that fills these directly avoids one host copy. */
@@ -133,16 +126,6 @@ int aeroddc_bank_host_slot(aeroddc_bank *bank, int slot, void **ptr, size_t *byt
  * broadcast): enqueues the kernels and the payload D2H on the bank's stream after `ready_event`
  * (a cudaEvent_t, may be NULL) and returns. Finish with aeroddc_bank_wait(). */
 int aeroddc_bank_submit_device(aeroddc_bank *bank, const void *dev_iq, size_t n_complex, void *ready_event);
-
-/* The same with the block spread over n_slices device buffers, slice i holding samples [i*slice_len, (i+1)*slice_len)
- * (the last one may be shorter). The buffers may live in the HBM of DIFFERENT GPUs (peer-mapped addresses: CUDA IPC
- * or cudaDeviceEnablePeerAccess): the main kernel's TMA tile loads then pull every tile from the GPU that holds it,
- * over NVLink, while computing - the multi-GPU exchange of the raw block fused into the
- * kernel, with no broadcast step and no staging copy; when every GPU of a node ingests 1/N of each block over its own
- * PCIe link, all N links and all N NVLink ports share the load. slice_len must be a multiple of 32 and >= 256;
- * n_slices <= 8. The kernels start after every event of ready_events[0..n_events) (cudaEvent_t, NULL entries skipped). */
-int aeroddc_bank_submit_device_sliced(aeroddc_bank *bank, const void *const *slices, int n_slices, size_t slice_len,
-                                      size_t n_complex, void *const *ready_events, int n_events);
 
 /* Payload of VFO `vfo` for the most recently completed block: pointer into pinned host memory
  * (valid until the next wait()/process()), its length in bytes and the output sample rate.
@@ -188,12 +171,9 @@ int aeroddc_measure_fp32_peak(int device, double *tflops, double *sm_clock_mhz);
 
 /* ------------------------------------------------------------------------------------------------
  * Fleet: one bank per GPU of a node, driven from ONE host thread.
- * VFOs are sharded over the devices (flat VFO i -> device i mod N; a main VFO takes its sub-VFOs with it), each GPU
- * runs its VFO subset and returns its own payloads. The raw block reaches the GPUs in one of two ways:
- *   peer (default): GPU i uploads slice i (1/N of the block) over its own PCIe link - N concurrent H2D copies - and
- *     every bank's kernel reads all slices in place through peer memory over NVLink (aeroddc_bank_submit_device_sliced);
- *   nccl (AERODDC_EXCHANGE=nccl, or no peer access): the block is uploaded once to devices[0] and broadcast to the
- *     others with ncclBroadcast over NVLink (libnccl.so.2 is loaded at run time).
+ * VFOs are sharded over the devices (flat VFO i -> device i mod N; a main VFO takes its sub-VFOs with it),
+ * every raw block is uploaded once to devices[0] and broadcast to the others with NCCL (ncclBroadcast over
+ * NVLink; libnccl.so.2 is loaded at run time), each GPU runs its VFO subset and returns its own payloads.
  * Same call order and error conventions as the bank; VFO indices are global (order of add_vfo).
  * Replaces, like the bank, Publisher::demodData -> vfo::process for every VFO (publisher.cpp:285-306).
  * ---------------------------------------------------------------------------------------------- */
@@ -205,16 +185,13 @@ int aeroddc_fleet_set_dc_correction(aeroddc_fleet *fleet, int enable);
 int aeroddc_fleet_finalize(aeroddc_fleet *fleet);
 /* Pinned host slot 0/1 of the ingest GPU's ring (fill it directly to avoid a host copy). */
 int aeroddc_fleet_host_slot(aeroddc_fleet *fleet, int slot, void **ptr, size_t *bytes);
-/* submit: the uploads (or upload + broadcast) + every GPU's kernels and payload D2H, asynchronously (at most two
- * blocks in flight); wait: the oldest submitted block's payloads are in host memory on every GPU. wait retires the
- * block on every GPU even when one reports an error; after any error the fleet refuses further blocks. */
+/* submit: H2D to devices[0] + NCCL broadcast + every GPU's kernels and payload D2H, asynchronously (at most two
+ * blocks in flight); wait: the oldest submitted block's payloads are in host memory on every GPU. */
 int aeroddc_fleet_submit(aeroddc_fleet *fleet, const void *host_iq, size_t n_complex);
 int aeroddc_fleet_wait(aeroddc_fleet *fleet);
 int aeroddc_fleet_process(aeroddc_fleet *fleet, const void *host_iq, size_t n_complex);
-int aeroddc_fleet_reset(aeroddc_fleet *fleet);   /* aeroddc_bank_reset on every GPU */
 int aeroddc_fleet_output(aeroddc_fleet *fleet, int vfo, const void **payload, size_t *nbytes, uint32_t *rate);
 int aeroddc_fleet_num_devices(aeroddc_fleet *fleet);
-int aeroddc_fleet_exchange(aeroddc_fleet *fleet);             /* 0 = single GPU, 1 = peer slices, 2 = NCCL broadcast */
 int aeroddc_fleet_device_of(aeroddc_fleet *fleet, int vfo);   /* index into the devices[] given at create */
 void aeroddc_fleet_destroy(aeroddc_fleet *fleet);
 
@@ -229,7 +206,6 @@ void aeroddc_fleet_destroy(aeroddc_fleet *fleet);
 int aeroddc_dev_alloc(int device, size_t bytes, void **dev_ptr);
 int aeroddc_dev_free(int device, void *dev_ptr);
 int aeroddc_dev_upload(int device, void *dev_ptr, const void *host, size_t bytes);   /* synchronous H2D */
-int aeroddc_dev_upload_async(int device, void *dev_ptr, const void *pinned_host, size_t bytes, void *stream);   /* cudaMemcpyAsync on a cudaStream_t */
 int aeroddc_ipc_export(int device, void *dev_ptr, unsigned char handle[AERODDC_IPC_HANDLE_BYTES]);
 int aeroddc_ipc_import(int device, const unsigned char handle[AERODDC_IPC_HANDLE_BYTES], void **dev_ptr);
 int aeroddc_ipc_close(int device, void *dev_ptr);

@@ -116,7 +116,7 @@ def test_segment_plan_invariants():
             assert p["segment_len"] % al == 0 and p["part_len"] % al == 0
             assert p["n_segments"] * p["segment_len"] >= blk > (p["n_segments"] - 1) * p["segment_len"]
             assert p["parts"] >= 1 and p["parts"] * p["part_len"] >= p["segment_len"]
-            assert p["segment_len"] >= 4 * p["warmup"]
+            assert p["segment_len"] >= 2 * p["warmup"]
             assert p["vfo_groups"] == -(-nv // 32)   # one warp of 32 VFOs per CTA
             per_group = p["ctas"] // p["vfo_groups"] - 1           # parts of all segments; the last segment may need fewer
             assert p["ctas"] % p["vfo_groups"] == 0 and p["n_segments"] <= per_group <= p["parts"] * p["n_segments"]
