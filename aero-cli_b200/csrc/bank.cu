@@ -695,7 +695,7 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
   CU(cudaMemcpy(b->d_tail, h_tail.data(), sizeof(TailVfo) * nv, cudaMemcpyHostToDevice));
 
   if (b->dcc) {
-    b->dcc_smem = (size_t)prop.sharedMemPerBlockOptin;   // everything an SM can give one CTA: no other CTA fits beside it
+    b->dcc_smem = (size_t)prop.sharedMemPerBlockOptin - 1024;   // (almost) everything an SM can give one CTA: no main-kernel CTA fits beside it
     CU(cudaFuncSetAttribute(dcc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->dcc_smem));
     CU(cudaFuncSetAttribute(dcc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->dcc_smem));
     CU(cudaFuncSetAttribute(dcc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->dcc_smem));
