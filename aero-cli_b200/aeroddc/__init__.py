@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libaeroddc.so")
 
 CU8, CS16, CF32 = 0, 1, 2
-MODE_EXACT, MODE_FAST = 0, 1
+MODE_EXACT, MODE_FAST, MODE_TENSOR = 0, 1, 2
 _NP_DTYPE = {CU8: np.uint8, CS16: np.int16, CF32: np.float32}
 
 

@@ -18,6 +18,7 @@
 
 #include "ddc_kernels.cuh"
 #include "aux_kernels.cuh"
+#include "tc_kernels.cuh"
 #include "design.h"
 
 namespace {
@@ -83,6 +84,8 @@ struct Group {   // VFOs sharing input stream and DA = min(D, 5): one launch of 
   size_t sched_words = 0;
   float2* d_hand = nullptr;
   float2* d_mid[2] = {nullptr, nullptr};   // [32-VFO group][n_mid][32], by block parity
+  uint4* d_filt = nullptr;     // tensor mode: per-VFO modulated composite filters, [tiles of 128 VFOs][40 k-steps][16 KB]
+  int tc_ntiles = 0;           // > 0: this group's bulk runs on ddc_tc_kernel
 };
 
 // cudaFuncSetAttribute is state of the (function, device) pair, shared by every bank of the process: a second bank with
@@ -133,6 +136,7 @@ struct aeroddc_bank {
   unsigned char* d_vfo_D = nullptr;                   // [vfo_pitch] half-band stages per column
   float2* d_xd = nullptr;       // all stage-D rows, per VFO: [hist][n_stage]
   float2** d_xd_rows = nullptr; // [vfo_pitch] pointer to stage-D index 0 of each column's row
+  float2* d_pw = nullptr;       // tensor mode: [kTcPwRows][vfo_pitch] unit rotation powers u^r
   int* d_nco_len = nullptr;     // [vfo_pitch]
   int* d_post_ctr = nullptr;    // work-item counters of the persistent post-processing kernels: [0] tail, [1 + g] deep kernel of group g
   int post_ctas_deep = 0, post_ctas_tail = 0;   // their grid sizes
@@ -209,7 +213,8 @@ void free_all(aeroddc_bank* b) {
   cudaFree(b->d_post_ctr);
   cudaFree(b->d_rot); cudaFree(b->d_qlast); cudaFree(b->d_ckpt); cudaFree(b->d_vfo_D);
   for (int i = 0; i < 3; ++i) cudaFree(b->d_state[i]);
-  for (Group& g : b->groups) { cudaFree(g.d_sched); cudaFree(g.d_hand); cudaFree(g.d_mid[0]); cudaFree(g.d_mid[1]); }
+  for (Group& g : b->groups) { cudaFree(g.d_sched); cudaFree(g.d_hand); cudaFree(g.d_mid[0]); cudaFree(g.d_mid[1]); cudaFree(g.d_filt); }
+  cudaFree(b->d_pw);
   if (b->h_err) cudaFreeHost((void*)b->h_err);
   cudaFree(b->d_dcc_out[0]); cudaFree(b->d_dcc_out[1]); cudaFree(b->d_dcc_state);
   cudaFree(b->d_xd); cudaFree(b->d_xd_rows); cudaFree(b->d_nco_len); cudaFree(b->d_taps); cudaFree(b->d_hil_idx); cudaFree(b->d_tail); cudaFree(b->d_out);
@@ -239,7 +244,7 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
   const int slot = (int)(k % 3);   // payload/event slot
   const int par = (int)(k & 1);
   cudaStream_t sA = b->s_compute, sB = b->s_post;
-  const bool fast = b->mode == AERODDC_MODE_FAST;
+  const bool fast = b->mode != AERODDC_MODE_EXACT;
   int launches = 0;
   RawBlock raw = raw_in;
   int raw_fmt = b->fmt;
@@ -331,10 +336,64 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
     p.sched = g.d_sched;
     p.hand = g.d_hand;
     p.err = b->d_err;
-    CU(cudaMemsetAsync(g.d_sched, 0, sizeof(int) * g.sched_words, sA));
-    dim3 grid((unsigned)(p.ngroups + g.nparts));
-    CU(launch_main(g.parent < 0 ? raw_fmt : AERODDC_CF32, g.DA, p, grid, sA, fast));
-    ++launches;
+    p.seg_off = 0;
+    p.cold0 = 0;
+    p.nbound = p.ngroups;
+    const int fmt_in = g.parent < 0 ? raw_fmt : AERODDC_CF32;
+    if (g.tc_ntiles > 0 && raw.n_slices == 1 && fmt_in == AERODDC_CF32) {
+      // Tensor mode. The FP32 kernel keeps what is not a clean FIR window: the head of the block (the half-band queues
+      // are re-seeded with a one-sample shift at every block start, dsp.cpp:163-172) and the zone after an oscillator
+      // restart (amplitude transient of the recurrence, oscillator.cpp:19-24); ddc_tc_kernel does every other output.
+      const int zone = kTcHead * 32;                                     // 2048 samples
+      const long long idx0 = p.block_abs % g.fs_in;
+      const long long wrap = idx0 == 0 ? 0 : (long long)g.fs_in - idx0;   // in-block sample at which the table restarts
+      int head = zone, fix_at = -1;
+      if (wrap > 0 && wrap < g.blk_in) {
+        const int a = (int)(wrap / kNcoStride) * kNcoStride;
+        if (a < zone) head = a + zone; else fix_at = a;
+      }
+      head = std::min(head, g.blk_in);
+      auto launch_range = [&](int off, int len, bool with_boundary) -> int {
+        MainParams r = p;
+        r.seg_off = off; r.S = len; r.P = len; r.nseg = 1; r.nchains = r.ngroups;
+        r.cold0 = off > 0; r.nbound = with_boundary ? r.ngroups : 0;
+        CU(cudaMemsetAsync(g.d_sched, 0, sizeof(int) * g.sched_words, sA));
+        CU(launch_main(AERODDC_CF32, g.DA, r, dim3((unsigned)(r.nbound + r.nchains)), sA, true));
+        ++launches;
+        return AERODDC_OK;
+      };
+      { const int rc = launch_range(0, head, true); if (rc != AERODDC_OK) return rc; }
+      if (head < g.blk_in) {
+        TcParams t;
+        t.raw = reinterpret_cast<const float2*>(p.raw.slice[0]);
+        t.filt = g.d_filt;
+        t.ckpt = b->d_ckpt;
+        t.pw = b->d_pw;
+        t.mid = g.d_mid[par];
+        t.block_abs = p.block_abs;
+        t.nco_len = g.fs_in;
+        t.nck = (g.fs_in + kNcoStride - 1) / kNcoStride;
+        t.vfo_pitch = b->vfo_pitch;
+        t.vfo_base = g.base;
+        t.vfo_count = g.count;
+        t.mid_groups = g.mid_pitch / 32;
+        t.n_mid = g.n_mid;
+        t.m_first = head / 32;
+        t.m_end = g.n_mid;
+        t.n_ntiles = g.tc_ntiles;
+        t.n_mtiles = (t.m_end - t.m_first + kTcM - 1) / kTcM;
+        const int tiles = t.n_ntiles * t.n_mtiles;
+        ddc_tc_kernel<<<(unsigned)std::min(tiles, b->n_sm), kTcThreads, kTcSmem, sA>>>(t);
+        CU(cudaGetLastError());
+        ++launches;
+      }
+      if (fix_at >= 0) { const int rc = launch_range(fix_at, zone, false); if (rc != AERODDC_OK) return rc; }
+    } else {
+      CU(cudaMemsetAsync(g.d_sched, 0, sizeof(int) * g.sched_words, sA));
+      dim3 grid((unsigned)(p.ngroups + g.nparts));
+      CU(launch_main(fmt_in, g.DA, p, grid, sA, fast));
+      ++launches;
+    }
     if (b->nested && !g.direct) { const int rc = launch_deep(g, sA); if (rc != AERODDC_OK) return rc; }
   }
   CU(cudaEventRecord(b->ev_m1[slot], sA));
@@ -465,7 +524,9 @@ int aeroddc_plan_segments(int block_len, int decim_count, int n_vfos, int n_sm, 
 int aeroddc_bank_set_mode(aeroddc_bank* b, int mode) {
   if (!b) return fail(AERODDC_ERR_ARG, "NULL bank");
   if (b->blocks_submitted > 0) return fail(AERODDC_ERR_STATE, "the arithmetic mode cannot change once blocks were processed");
-  if (mode != AERODDC_MODE_EXACT && mode != AERODDC_MODE_FAST) return fail(AERODDC_ERR_ARG, "unknown mode %d", mode);
+  if (mode != AERODDC_MODE_EXACT && mode != AERODDC_MODE_FAST && mode != AERODDC_MODE_TENSOR) return fail(AERODDC_ERR_ARG, "unknown mode %d", mode);
+  if (mode == AERODDC_MODE_TENSOR && b->finalized) return fail(AERODDC_ERR_STATE, "AERODDC_MODE_TENSOR must be chosen before finalize (its filter tables are built there)");
+  if (b->mode == AERODDC_MODE_TENSOR && mode != AERODDC_MODE_TENSOR && b->finalized) return fail(AERODDC_ERR_STATE, "the bank was finalized for AERODDC_MODE_TENSOR");
   b->mode = mode;
   return AERODDC_OK;
 }
@@ -747,6 +808,45 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
         b->d_rot, b->d_nco_len, b->d_ckpt, b->d_qlast, b->vfo_pitch, b->vfo_pitch, kNcoStride);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(b->s_compute));
+  }
+  // ---- tensor mode: per-VFO modulated composite filters and rotation powers ----
+  if (b->mode == AERODDC_MODE_TENSOR) {
+    // g = the five half-band stages as one FIR decimating by 32: h (*) up2(h) (*) up4(h) (*) up8(h) (*) up16(h), 311 taps
+    const double h11[11] = {HB_P0, 0, HB_P2, 0, HB_P4, HB_P5, HB_P4, 0, HB_P2, 0, HB_P0};
+    std::vector<double> g5(h11, h11 + 11);
+    for (int s = 1; s < kFastStages; ++s) {
+      std::vector<double> up((10 << s) + 1, 0.0), nx(g5.size() + (10 << s), 0.0);
+      for (int i = 0; i < 11; ++i) up[(size_t)i << s] = h11[i];
+      for (size_t i = 0; i < g5.size(); ++i)
+        for (size_t j = 0; j < up.size(); ++j) nx[i + j] += g5[i] * up[j];
+      g5.swap(nx);
+    }
+    if ((int)g5.size() != kTcTaps) return fail(AERODDC_ERR_DESIGN, "composite half-band response has %zu taps", g5.size());
+    double* d_g = nullptr;
+    bool any = false;
+    for (Group& g : b->groups) {
+      if (g.parent >= 0 || g.DA != kFastStages || g.direct) continue;          // raw-fed groups with deep stages only
+      if (!(b->fmt == AERODDC_CF32 || b->dcc)) continue;                       // the X tiles are staged from cf32
+      if (g.blk_in < 4 * kTcHead * 32) continue;
+      if (!d_g) {
+        CU(cudaMalloc((void**)&d_g, sizeof(double) * kTcTaps));
+        CU(cudaMemcpy(d_g, g5.data(), sizeof(double) * kTcTaps, cudaMemcpyHostToDevice));
+      }
+      g.tc_ntiles = (g.count + kTcVfos - 1) / kTcVfos;
+      CU(dmalloc((void**)&g.d_filt, (size_t)g.tc_ntiles * kTcKSteps * kTcFSlab));
+      const int n = g.tc_ntiles * kTcKSteps * kTcN;
+      tc_build_filters_kernel<<<(n + 127) / 128, 128, 0, b->s_compute>>>(b->d_rot, d_g, g.base, g.count, g.tc_ntiles, g.d_filt);
+      CU(cudaGetLastError());
+      any = true;
+    }
+    if (any) {
+      CU(dmalloc((void**)&b->d_pw, sizeof(float2) * (size_t)kTcPwRows * b->vfo_pitch));
+      tc_build_pw_kernel<<<dim3((b->vfo_pitch + 127) / 128, kTcPwRows), 128, 0, b->s_compute>>>(b->d_rot, b->vfo_pitch, b->d_pw);
+      CU(cudaGetLastError());
+      CU(cudaFuncSetAttribute(ddc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
+      CU(cudaStreamSynchronize(b->s_compute));
+    }
+    if (d_g) cudaFree(d_g);
   }
   b->dev_bytes = bytes;
   b->finalized = true;

@@ -206,6 +206,10 @@ struct MainParams {
                              // (chain + 1 per entry); zeroed by the host before every launch
   float2* hand;              // [nchains][kHandSlots][kThreads]
   int* err;                  // set to 1 if a CTA gave up waiting for its queue entry (should never happen)
+  // A launch may cover only a stretch of the block (tensor mode keeps the head of every block and the zone after an
+  // oscillator restart on this kernel): segment k starts at seg_off + k*S; cold0 = segment 0 does not continue the saved
+  // block history but runs in over W samples like the others; nbound = boundary CTAs of this launch (ngroups or 0).
+  int seg_off, cold0, nbound;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -432,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
 
   const int tid = threadIdx.x;
   // 1-D grid of anonymous CTAs; a CTA finds out what it is when it STARTS. Item t (an atomic counter) is: the boundary
-  // role of VFO group t for t < ngroups; part 0 of chain t - ngroups for the next nchains items; after that, entry
+  // role of VFO group t for t < nbound (= ngroups); part 0 of chain t - ngroups for the next nchains items; after that, entry
   // t - ngroups - nchains of the ready queue, i.e. the next part of whichever chain was handed on at that position.
   // Every entry below t has been taken by a CTA that started earlier and is resident or finished, so the entry this
   // CTA waits for is always on its way - whatever order the hardware dispatches blocks in.
@@ -442,12 +446,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
   if (tid == 0) {
     int chain = 0, q = 0;
     const int t = atomicAdd(p.sched, 1);
-    if (t < p.ngroups) {
+    if (t < p.nbound) {
       chain = -1 - t;
-    } else if (t < p.ngroups + p.nchains) {
-      chain = t - p.ngroups;
+    } else if (t < p.nbound + p.nchains) {
+      chain = t - p.nbound;
     } else {
-      const int* entry = p.sched + 2 + p.nchains + (t - p.ngroups - p.nchains);
+      const int* entry = p.sched + 2 + p.nchains + (t - p.nbound - p.nchains);
       int v, spins = 0;
       do {
         asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(entry) : "memory");
@@ -475,11 +479,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
     return;
   }
 
-  const int seg_start = seg * p.S;
+  const int seg_start = p.seg_off + seg * p.S;
   const int seg_end = min(seg_start + p.S, p.B);
   const int part_start = seg_start + q * p.P;
   const int part_end = min(part_start + p.P, seg_end);
-  const int warm = (q > 0 || seg == 0) ? 0 : p.W;         // part 0 of segment 0 starts from the saved block history
+  const bool from_history = seg == 0 && !p.cold0;         // part 0 of segment 0 starts from the saved block history
+  const int warm = (q > 0 || from_history) ? 0 : p.W;
   const int first = part_start - warm;                    // in-block index of the first sample processed
   const int total = warm + (part_end - part_start);       // multiple of max(kChunk, 2^DA)
   const int ntiles = (total + kTile - 1) / kTile;
@@ -525,7 +530,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ddc_main_kernel(const Ma
 #pragma unroll
       for (int k = 0; k < 3; ++k) hb[s].o[k] = load_p2_cg(hand + (size_t)(s * kStateSlots + 5 + k) * kThreads);
     }
-  } else if (seg == 0) {
+  } else if (from_history) {
 #pragma unroll
     for (int s = 0; s < NF; ++s) {
       const float2* st = p.state_in + (size_t)s * kStateSlots * p.vfo_pitch + vfo;
