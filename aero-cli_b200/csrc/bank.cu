@@ -136,6 +136,7 @@ struct aeroddc_bank {
   unsigned char* d_vfo_D = nullptr;                   // [vfo_pitch] half-band stages per column
   float2* d_xd = nullptr;       // all stage-D rows, per VFO: [hist][n_stage]
   float2** d_xd_rows = nullptr; // [vfo_pitch] pointer to stage-D index 0 of each column's row
+  int tc_fstages = 9;
   float2* d_pw = nullptr;       // tensor mode: [kTcPwRows][vfo_pitch] unit rotation powers u^r
   int* d_nco_len = nullptr;     // [vfo_pitch]
   int* d_post_ctr = nullptr;    // work-item counters of the persistent post-processing kernels: [0] tail, [1 + g] deep kernel of group g
@@ -340,7 +341,7 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
     p.cold0 = 0;
     p.nbound = p.ngroups;
     const int fmt_in = g.parent < 0 ? raw_fmt : AERODDC_CF32;
-    if (g.tc_ntiles > 0 && raw.n_slices == 1 && fmt_in == AERODDC_CF32) {
+    if (g.tc_ntiles > 0 && fmt_in == AERODDC_CF32) {
       // Tensor mode. The FP32 kernel keeps what is not a clean FIR window: the head of the block (the half-band queues
       // are re-seeded with a one-sample shift at every block start, dsp.cpp:163-172) and the zone after an oscillator
       // restart (amplitude transient of the recurrence, oscillator.cpp:19-24); ddc_tc_kernel does every other output.
@@ -365,7 +366,7 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
       { const int rc = launch_range(0, head, true); if (rc != AERODDC_OK) return rc; }
       if (head < g.blk_in) {
         TcParams t;
-        t.raw = reinterpret_cast<const float2*>(p.raw.slice[0]);
+        t.raw = p.raw;
         t.filt = g.d_filt;
         t.ckpt = b->d_ckpt;
         t.pw = b->d_pw;
@@ -383,7 +384,8 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
         t.n_ntiles = g.tc_ntiles;
         t.n_mtiles = (t.m_end - t.m_first + kTcM - 1) / kTcM;
         const int tiles = t.n_ntiles * t.n_mtiles;
-        ddc_tc_kernel<<<(unsigned)std::min(tiles, b->n_sm), kTcThreads, kTcSmem, sA>>>(t);
+        if (b->tc_fstages == 6) ddc_tc_kernel<6><<<(unsigned)std::min(tiles, b->n_sm), kTcThreads, TcSmem<6>::kTotal, sA>>>(t);
+        else ddc_tc_kernel<9><<<(unsigned)std::min(tiles, b->n_sm), kTcThreads, TcSmem<9>::kTotal, sA>>>(t);
         CU(cudaGetLastError());
         ++launches;
       }
@@ -843,7 +845,10 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
       CU(dmalloc((void**)&b->d_pw, sizeof(float2) * (size_t)kTcPwRows * b->vfo_pitch));
       tc_build_pw_kernel<<<dim3((b->vfo_pitch + 127) / 128, kTcPwRows), 128, 0, b->s_compute>>>(b->d_rot, b->vfo_pitch, b->d_pw);
       CU(cudaGetLastError());
-      CU(cudaFuncSetAttribute(ddc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
+      const char* env_fs = getenv("AERODDC_TC_FSTAGES");   // experiments: depth of the filter-slab ring (6 or 9)
+      b->tc_fstages = env_fs && atoi(env_fs) == 6 ? 6 : 9;
+      CU(cudaFuncSetAttribute(ddc_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<6>::kTotal));
+      CU(cudaFuncSetAttribute(ddc_tc_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<9>::kTotal));
       CU(cudaStreamSynchronize(b->s_compute));
     }
     if (d_g) cudaFree(d_g);

@@ -48,15 +48,16 @@ constexpr int kTcXStage = 2 * kTcXPart;               // hi | mid
 constexpr int kTcXStages = 2;
 constexpr int kTcFPart = 2 * kTcN * 16;               // one bf16 part of a filter slab: [2 chunks][256 rails][16 B]
 constexpr int kTcFSlab = 2 * kTcFPart;                // hi | mid
-constexpr int kTcFStages = 6;
-constexpr int kTcBars = 2 * kTcXStages + 2 * kTcFStages + 4;
-constexpr int kTcSmem = kTcXStages * kTcXStage + kTcFStages * kTcFSlab + 8 * kTcBars + 16;
+template <int FS> struct TcSmem {   // FS = filter-slab ring depth
+  static constexpr int kBars = 2 * kTcXStages + 2 * FS + 4;
+  static constexpr int kTotal = kTcXStages * kTcXStage + FS * kTcFSlab + 8 * kBars + 16;
+};
 constexpr int kTcThreads = 320;
 constexpr int kTcPwRows = 512;            // rotation table rows: u^r, r = 0 .. 511
 constexpr int kTcHead = 64;               // outputs [0, kTcHead) of a block (2048 samples) stay on the FP32 kernel
 
 struct TcParams {
-  const float2* raw;          // the block (cf32, one slice)
+  RawBlock raw;               // the block (cf32), possibly in slices on several GPUs (a 32-sample row never straddles slices)
   const uint4* filt;          // [n_ntiles][kTcKSteps][kTcFSlab / 16]
   const float2* ckpt;         // [nck][vfo_pitch] exact NCO checkpoints (state after 256 k steps)
   const float2* pw;           // [kTcPwRows][vfo_pitch] u^r
@@ -112,7 +113,9 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   mid = *reinterpret_cast<const uint32_t*>(&m);
 }
 
+template <int kTcFStages>
 __global__ void __launch_bounds__(kTcThreads, 1) ddc_tc_kernel(const TcParams p) {
+  constexpr int kTcBars = TcSmem<kTcFStages>::kBars;
   extern __shared__ __align__(1024) unsigned char tsm[];
   unsigned char* xs = tsm;
   unsigned char* fsl = tsm + kTcXStages * kTcXStage;
@@ -202,7 +205,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) ddc_tc_kernel(const TcParams p)
       for (int i = ptid; i < kTcM + kTcBack; i += 128) {
         const int rho = row0 + i;
         const bool valid = rho >= 0 && rho < p.n_mid;
-        const float4* src = reinterpret_cast<const float4*>(p.raw + (size_t)(valid ? rho : 0) * 32);
+        const int g0 = (valid ? rho : 0) * 32;
+        const int sl = p.raw.n_slices > 1 ? g0 / p.raw.slice_len : 0;
+        const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(p.raw.slice[sl]) + (g0 - sl * p.raw.slice_len));
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float4 u = make_float4(0.f, 0.f, 0.f, 0.f), w = u;

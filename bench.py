@@ -390,6 +390,7 @@ def main():
     ap.add_argument("--vfos", type=int, default=N_VFOS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast", action="store_true", help="skip the tolerance-mode side measurement")
+    ap.add_argument("--no-tensor", action="store_true", help="skip the tensor-mode side measurement")
     ap.add_argument("--no-parity", action="store_true", help="skip the byte-identity leg (never skipped by default)")
     ap.add_argument("--no-side", action="store_true", help="skip the side lines for BASELINE configs[0..2] and DC correction (N = 1 only)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
@@ -600,31 +601,41 @@ def main():
 
     # ---- parity: the same bank, rewound, six distinct blocks through the same device path, against the reference chain ----
     parity = None
-    if not args.no_parity:
-        n = len(mine)
-        picks = sorted(set([0, n - 1] + [int(round(i * (n - 1) / 7.0)) for i in range(1, 7)]))
-        bank.reset()
-        pblocks = [parity_block(k) for k in range(PARITY_BLOCKS)]
+    n_mine = len(mine)
+    picks = sorted(set([0, n_mine - 1] + [int(round(i * (n_mine - 1) / 7.0)) for i in range(1, 7)]))
+
+    def feed_parity_blocks(bk):
+        """Rewind bank bk and feed it the six parity blocks through the device path that was timed; returns got[j][k] = payload
+        bytes of VFO picks[j], block k."""
+        bk.reset()
         got = [[] for _ in picks]
-        for k, x in enumerate(pblocks):
+        for k in range(PARITY_BLOCKS):
+            x = parity_block(k)
             if world == 1:
                 dbuf[k & 1].copy_(torch.from_numpy(x))
                 torch.cuda.synchronize()
-                bank.submit_device(dbuf[k & 1].data_ptr(), None)
+                bk.submit_device(dbuf[k & 1].data_ptr(), None)
             elif peer:
                 upload_my_slice(k % RING, x, blocking=True)
                 host_barrier()
-                bank.submit_device_sliced(ring_ptrs[k % RING], slice_len)
+                bk.submit_device_sliced(ring_ptrs[k % RING], slice_len)
             else:
                 if rank == 0:
                     dbuf[k & 1].copy_(torch.from_numpy(x))
                 dist.broadcast(dbuf[k & 1], src=0)
                 torch.cuda.synchronize()
-                bank.submit_device(dbuf[k & 1].data_ptr(), None)
-            bank.wait()
+                bk.submit_device(dbuf[k & 1].data_ptr(), None)
+            bk.wait()
             host_barrier()
             for j, i in enumerate(picks):
-                got[j].append(bank.output(i)[0])
+                got[j].append(bk.output(i)[0])
+        return got
+
+    exact_payloads = None
+    if not args.no_parity:
+        got = feed_parity_blocks(bank)
+        exact_payloads = got
+        pblocks = [parity_block(k) for k in range(PARITY_BLOCKS)]
         kind, bad = parity_check(pblocks, [(DECIM, LATE, float(freqs[mine[i]]), GAIN) for i in picks], got)
         nz = sum(1 for g in got for p in g if any(p))
         parity = {"vfos": len(picks), "blocks": PARITY_BLOCKS, "byte_identical": not bad, "mismatches": len(bad),
@@ -646,6 +657,34 @@ def main():
         sync_all()
         fbank.close()
 
+    # ---- tensor mode (AERODDC_MODE_TENSOR): mix + five half-band stages as a complex GEMM on tcgen05 ----
+    tens = None
+    if not args.no_tensor:
+        tbank = make_bank(mode=aeroddc.MODE_TENSOR)
+        t_main = []
+        run_blocks(tbank, args.warmup, False)
+        sync_all()
+        tbank.stopwatch_start(False)
+        run_blocks(tbank, args.steps, False, on_wait=lambda: t_main.append(tbank.last_main_ms()))
+        t_ms = tbank.stopwatch_stop()
+        sync_all()
+        t_launches = tbank.last_timing()[1]
+        run_blocks(tbank, 3, True)
+        sync_all()
+        t0 = time.perf_counter()
+        run_blocks(tbank, args.steps, True)
+        sync_all()
+        t_e2e_ms = (time.perf_counter() - t0) * 1e3
+        tens = {"ms": t_ms, "e2e_ms": t_e2e_ms, "main_ms": float(np.mean(t_main)), "launches": t_launches, "tol": None}
+        if exact_payloads is not None:
+            # tolerance against the payloads the exact mode produced for the same six blocks (which equal the reference's byte for byte)
+            tgot = feed_parity_blocks(tbank)
+            e = np.concatenate([np.frombuffer(a, np.int16).astype(np.float64) - np.frombuffer(b, np.int16).astype(np.float64)
+                                for ga, gb in zip(tgot, exact_payloads) for a, b in zip(ga, gb)])
+            r = np.concatenate([np.frombuffer(b, np.int16).astype(np.float64) for gb in exact_payloads for b in gb])
+            tens["tol"] = {"max_abs_err_lsb": float(np.abs(e).max()), "err_power": float((e ** 2).sum()), "ref_power": float((r ** 2).sum()), "n": int(e.size)}
+        tbank.close()
+
     # ---- DC correction on (publisher.cpp:292-296): the sequential recurrence runs one block ahead on its own stream ----
     dcc_ms = None
     if not args.no_side and world == 1:
@@ -659,10 +698,17 @@ def main():
         dbank.close()
 
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_ms, wall_ms, fast_ms or 0.0], dtype=torch.float64, device=dev)
+        t = torch.tensor([dev_ms, e2e_ms, wall_ms, fast_ms or 0.0, tens["ms"] if tens else 0.0, tens["e2e_ms"] if tens else 0.0,
+                          tens["tol"]["max_abs_err_lsb"] if tens and tens["tol"] else 0.0], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms, wall_ms, fast_ms_r = [float(v) for v in t.tolist()]
+        dev_ms, e2e_ms, wall_ms, fast_ms_r, tens_ms_r, tens_e2e_r, tens_err_r = [float(v) for v in t.tolist()]
         fast_ms = fast_ms_r if fast_ms is not None else None
+        if tens:
+            tens["ms"], tens["e2e_ms"] = tens_ms_r, tens_e2e_r
+            if tens["tol"]:
+                pw = torch.tensor([tens["tol"]["err_power"], tens["tol"]["ref_power"], float(tens["tol"]["n"])], dtype=torch.float64, device=dev)
+                dist.all_reduce(pw)
+                tens["tol"] = {"max_abs_err_lsb": tens_err_r, "err_power": float(pw[0]), "ref_power": float(pw[1]), "n": int(pw[2])}
         n_mine = torch.tensor([len(mine)], dtype=torch.int64, device=dev)
         dist.all_reduce(n_mine)
         assert int(n_mine.item()) == args.vfos
@@ -717,7 +763,7 @@ def main():
             "e2e": {"value": e2e, "unit": "Gsps", "h2d_bytes_per_step": BLOCK * 8,
                     "d2h_bytes_per_step": int(args.vfos * (BLOCK >> DECIM) // LATE * 2),
                     "note": "pinned host blocks, two blocks in flight, H2D of every block (N > 1: 1/N per GPU, concurrently) and D2H of every payload inside; wall clock between device syncs"},
-            "gpu_launches": int(launches_per_step * args.steps * (2 if fast_ms is None else 3)),
+            "gpu_launches": int(launches_per_step * args.steps * (2 if fast_ms is None else 3) + (2 * tens["launches"] * args.steps if tens else 0)),
             "roofline": {
                 "bound": "fp32", "kernel": "ddc_main_kernel", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                 "frac": achieved / peak_tflops, "traffic": traffic,
@@ -739,6 +785,32 @@ def main():
                         "tests/test_e2e_decode.py); the headline value above is the byte-identical mode"},
             "wall_ms_per_step": wall_ms / args.steps,
         }
+        if tens:
+            mma_flop = 3 * 2.0 * 256 * 128 * 640            # three bf16 products per k-step, M=128 x N=256 x K=640 per tile
+            tiles = -(-len(mine) // 128) * -(-((BLOCK >> 5) - 64) // 128)
+            tol = tens["tol"]
+            bf16_peak = None
+            if os.path.exists(mp):
+                bf16_peak = json.load(open(mp)).get("bf16_tflops_sustained")
+            line["tensor_mode"] = {
+                "value": total / (tens["ms"] * 1e-3) / 1e9, "unit": "Gsps", "ms_per_step": tens["ms"] / args.steps,
+                "e2e": {"value": total / (tens["e2e_ms"] * 1e-3) / 1e9, "unit": "Gsps", "h2d_bytes_per_step": BLOCK * 8,
+                        "d2h_bytes_per_step": int(args.vfos * (BLOCK >> DECIM) // LATE * 2)},
+                "realtime_x": total / (tens["ms"] * 1e-3) / (args.vfos * FS),
+                "main_ms": tens["main_ms"], "launches_per_step": tens["launches"],
+                "roofline": {"bound": "tensor", "kernel": "ddc_tc_kernel (+ the FP32 head launch)", "unit": "TFLOP/s",
+                             "achieved": tiles * mma_flop / (tens["main_ms"] * 1e-3) / 1e12, "peak": bf16_peak,
+                             "frac": (tiles * mma_flop / (tens["main_ms"] * 1e-3) / 1e12 / bf16_peak) if bf16_peak else None,
+                             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, back to back)",
+                             "note": "achieved = bf16 MMA flops issued (3 products of the hi+mid operand split, K padded 311 -> 320 taps) / time of the "
+                                     "main-stream kernels of a step; the path's algorithmic work is %.1f flop per VFO-sample (FP32 formulation)" % FLOPS_MAIN},
+                "tolerance_vs_exact": None if tol is None else {
+                    "vfos": parity["vfos"] if parity else None, "blocks": PARITY_BLOCKS, "int16_max_abs_err_lsb": tol["max_abs_err_lsb"],
+                    "int16_max_abs_err_fs": tol["max_abs_err_lsb"] / 32768.0,
+                    "int16_err_snr_db": float(10 * np.log10(tol["ref_power"] / max(tol["err_power"], 1e-30))),
+                    "bound": "max|err| <= 1e-4 FS (3.3 LSB), SNR >= 80 dB (BASELINE.json north_star)"},
+                "note": "AERODDC_MODE_TENSOR: NCO mix + half-band stages 0-4 as one complex GEMM on tcgen05 (bf16 hi+mid operand split, fp32 TMEM accumulators); block heads and "
+                        "oscillator-restart zones on the FP32 kernel; NOT bit-identical - tolerance mode, decoded frames identical (tests/test_e2e_decode.py); the headline value is the byte-identical mode"}
         if dcc_ms is not None:
             line["dc_correction"] = {"value": float(args.vfos) * BLOCK / (dcc_ms * 1e-3) / 1e9, "unit": "Gsps", "ms_per_step": dcc_ms,
                                      "realtime_x": 250.0 / dcc_ms,

@@ -89,7 +89,7 @@ int aeroddc_plan_segments(int block_len, int decim_count, int n_vfos, int n_sm, 
  *   AERODDC_MODE_TENSOR: the mix and the first five half-band stages as one complex GEMM on the 5th-generation
  *       tensor cores (tcgen05, bf16 hi+mid operand split, fp32 accumulation in TMEM; csrc/tc_kernels.cuh); same
  *       tolerance class as AERODDC_MODE_FAST. Applies to VFOs with decim_count >= 5 fed by the bank's raw cf32
- *       stream (or any format with DC correction on) given as one slice; every other VFO, the head of each block
+ *       stream (or any format with DC correction on); every other VFO, the head of each block
  *       and the zone after an oscillator-table restart run as in AERODDC_MODE_FAST. Set before finalize. */
 enum { AERODDC_MODE_EXACT = 0, AERODDC_MODE_FAST = 1, AERODDC_MODE_TENSOR = 2 };
 int aeroddc_bank_set_mode(aeroddc_bank *bank, int mode);

@@ -1,5 +1,5 @@
 """Tensor mode against the exact mode on the GPU (scratch): stage-D error, payload error, kernel time.
-usage: python scratch/tc_check.py [n_vfos] [fs] [block] [blocks]"""
+usage: python scratch/tc_check.py [n_vfos] [fs] [block] [blocks] [late] [tensor-only]"""
 import sys, time
 sys.path.insert(0, 'tests'); sys.path.insert(0, 'aero-cli_b200')
 import numpy as np, aeroddc
@@ -8,7 +8,9 @@ nv = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 fs = int(sys.argv[2]) if len(sys.argv) > 2 else 61440000
 blk = int(sys.argv[3]) if len(sys.argv) > 3 else fs // 4
 nblocks = int(sys.argv[4]) if len(sys.argv) > 4 else 3
-D, L, G = 8, 5, 0.05
+D, G = 8, 0.05
+L = int(sys.argv[5]) if len(sys.argv) > 5 else 5
+only_tensor = len(sys.argv) > 6
 rng = np.random.default_rng(5)
 freqs = rng.integers(int(-0.45 * fs), int(0.45 * fs), nv).astype(np.float64)
 
@@ -37,6 +39,10 @@ def run(mode):
     b.close()
     return outs, stages, ms
 
+if only_tensor:
+    got = run(aeroddc.MODE_TENSOR)
+    print("tensor only: main ms per block", ["%.3f" % m for m in got[2]])
+    sys.exit(0)
 ref = run(aeroddc.MODE_EXACT)
 for name, mode in (("fast", aeroddc.MODE_FAST), ("tensor", aeroddc.MODE_TENSOR)):
     t0 = time.time()
