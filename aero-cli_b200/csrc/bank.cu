@@ -84,8 +84,11 @@ struct Group {   // VFOs sharing input stream and DA = min(D, 5): one launch of 
   size_t sched_words = 0;
   float2* d_hand = nullptr;
   float2* d_mid[2] = {nullptr, nullptr};   // [32-VFO group][n_mid][32], by block parity
-  uint4* d_filt = nullptr;     // tensor mode: per-VFO modulated composite filters, [tiles of 128 VFOs][40 k-steps][16 KB]
-  int tc_ntiles = 0;           // > 0: this group's bulk runs on ddc_tc_kernel
+  uint4* d_filt = nullptr;     // tensor mode: per-VFO modulated composite filters, [tiles of 64 VFOs][40 k-steps][8 KB]
+  int tc_ntiles = 0;           // > 0: this group runs on ddc_tc_kernel (all but the zones, which stay on the FP32 kernel)
+  TcSeg* d_segs = nullptr;     // host-planned stretches of the (VFO tile, time) plane, one run of them per CTA
+  int* d_cta_seg = nullptr;
+  int tc_grid = 0;
 };
 
 // cudaFuncSetAttribute is state of the (function, device) pair, shared by every bank of the process: a second bank with
@@ -136,7 +139,6 @@ struct aeroddc_bank {
   unsigned char* d_vfo_D = nullptr;                   // [vfo_pitch] half-band stages per column
   float2* d_xd = nullptr;       // all stage-D rows, per VFO: [hist][n_stage]
   float2** d_xd_rows = nullptr; // [vfo_pitch] pointer to stage-D index 0 of each column's row
-  int tc_fstages = 9;
   float2* d_pw = nullptr;       // tensor mode: [kTcPwRows][vfo_pitch] unit rotation powers u^r
   int* d_nco_len = nullptr;     // [vfo_pitch]
   int* d_post_ctr = nullptr;    // work-item counters of the persistent post-processing kernels: [0] tail, [1 + g] deep kernel of group g
@@ -161,6 +163,7 @@ struct aeroddc_bank {
   // s_compute: main kernels. s_post: deep + tail + history shift of block k, overlapping the main kernel of block k+1
   // (== s_compute for nested banks). s_dcc: DC removal one block ahead. s_copy: H2D of raw blocks. s_d2h: payloads out.
   cudaStream_t s_compute = nullptr, s_post = nullptr, s_dcc = nullptr, s_copy = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_post[2] = {};   // tail + history shift of parity p finished (the stage-D rows may be overwritten)
   cudaEvent_t ev_main[2] = {};   // main kernels of parity p finished
   cudaEvent_t ev_dcc[2] = {};    // corrected block of parity p ready
   cudaEvent_t ev_tail[2] = {};   // payload rows of parity p written
@@ -214,7 +217,7 @@ void free_all(aeroddc_bank* b) {
   cudaFree(b->d_post_ctr);
   cudaFree(b->d_rot); cudaFree(b->d_qlast); cudaFree(b->d_ckpt); cudaFree(b->d_vfo_D);
   for (int i = 0; i < 3; ++i) cudaFree(b->d_state[i]);
-  for (Group& g : b->groups) { cudaFree(g.d_sched); cudaFree(g.d_hand); cudaFree(g.d_mid[0]); cudaFree(g.d_mid[1]); cudaFree(g.d_filt); }
+  for (Group& g : b->groups) { cudaFree(g.d_sched); cudaFree(g.d_hand); cudaFree(g.d_mid[0]); cudaFree(g.d_mid[1]); cudaFree(g.d_filt); cudaFree(g.d_segs); cudaFree(g.d_cta_seg); }
   cudaFree(b->d_pw);
   if (b->h_err) cudaFreeHost((void*)b->h_err);
   cudaFree(b->d_dcc_out[0]); cudaFree(b->d_dcc_out[1]); cudaFree(b->d_dcc_state);
@@ -222,7 +225,7 @@ void free_all(aeroddc_bank* b) {
   cudaFree(b->d_in[0]); cudaFree(b->d_in[1]);
   for (int i = 0; i < 2; ++i) {
     if (b->h_in[i]) cudaFreeHost(b->h_in[i]);
-    for (cudaEvent_t e : {b->ev_h2d[i], b->ev_tail[i], b->ev_d2h[i], b->ev_main[i], b->ev_dcc[i]}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {b->ev_h2d[i], b->ev_tail[i], b->ev_d2h[i], b->ev_main[i], b->ev_dcc[i], b->ev_post[i]}) if (e) cudaEventDestroy(e);
   }
   for (int i = 0; i < 3; ++i) {
     if (b->h_out[i]) cudaFreeHost(b->h_out[i]);
@@ -341,10 +344,11 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
     p.cold0 = 0;
     p.nbound = p.ngroups;
     const int fmt_in = g.parent < 0 ? raw_fmt : AERODDC_CF32;
-    if (g.tc_ntiles > 0 && fmt_in == AERODDC_CF32) {
+    if (g.tc_ntiles > 0) {
       // Tensor mode. The FP32 kernel keeps what is not a clean FIR window: the head of the block (the half-band queues
       // are re-seeded with a one-sample shift at every block start, dsp.cpp:163-172) and the zone after an oscillator
-      // restart (amplitude transient of the recurrence, oscillator.cpp:19-24); ddc_tc_kernel does every other output.
+      // restart (amplitude transient of the recurrence, oscillator.cpp:19-24); its stage-5 samples go to the mid stream,
+      // where ddc_tc_kernel - which does every other output and all the later stages - picks them up.
       const int zone = kTcHead * 32;                                     // 2048 samples
       const long long idx0 = p.block_abs % g.fs_in;
       const long long wrap = idx0 == 0 ? 0 : (long long)g.fs_in - idx0;   // in-block sample at which the table restarts
@@ -356,6 +360,7 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
       head = std::min(head, g.blk_in);
       auto launch_range = [&](int off, int len, bool with_boundary) -> int {
         MainParams r = p;
+        r.mid = g.d_mid[par];
         r.seg_off = off; r.S = len; r.P = len; r.nseg = 1; r.nchains = r.ngroups;
         r.cold0 = off > 0; r.nbound = with_boundary ? r.ngroups : 0;
         CU(cudaMemsetAsync(g.d_sched, 0, sizeof(int) * g.sched_words, sA));
@@ -364,46 +369,48 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
         return AERODDC_OK;
       };
       { const int rc = launch_range(0, head, true); if (rc != AERODDC_OK) return rc; }
-      if (head < g.blk_in) {
-        TcParams t;
-        t.raw = p.raw;
-        t.filt = g.d_filt;
-        t.ckpt = b->d_ckpt;
-        t.pw = b->d_pw;
-        t.mid = g.d_mid[par];
-        t.block_abs = p.block_abs;
-        t.nco_len = g.fs_in;
-        t.nck = (g.fs_in + kNcoStride - 1) / kNcoStride;
-        t.vfo_pitch = b->vfo_pitch;
-        t.vfo_base = g.base;
-        t.vfo_count = g.count;
-        t.mid_groups = g.mid_pitch / 32;
-        t.n_mid = g.n_mid;
-        t.m_first = head / 32;
-        t.m_end = g.n_mid;
-        t.n_ntiles = g.tc_ntiles;
-        t.n_mtiles = (t.m_end - t.m_first + kTcM - 1) / kTcM;
-        const int tiles = t.n_ntiles * t.n_mtiles;
-        if (b->tc_fstages == 6) ddc_tc_kernel<6><<<(unsigned)std::min(tiles, b->n_sm), kTcThreads, TcSmem<6>::kTotal, sA>>>(t);
-        else ddc_tc_kernel<9><<<(unsigned)std::min(tiles, b->n_sm), kTcThreads, TcSmem<9>::kTotal, sA>>>(t);
-        CU(cudaGetLastError());
-        ++launches;
-      }
       if (fix_at >= 0) { const int rc = launch_range(fix_at, zone, false); if (rc != AERODDC_OK) return rc; }
+      TcParams t;
+      t.raw = p.raw;
+      t.filt = g.d_filt;
+      t.ckpt = b->d_ckpt;
+      t.pw = b->d_pw;
+      t.zone = g.d_mid[par];
+      t.state_in = state_in;
+      t.state_out = state_out;
+      t.xd_rows = b->d_xd_rows;
+      t.vfo_D = b->d_vfo_D;
+      t.segs = g.d_segs;
+      t.cta_seg = g.d_cta_seg;
+      t.block_abs = p.block_abs;
+      t.nco_len = g.fs_in;
+      t.nck = (g.fs_in + kNcoStride - 1) / kNcoStride;
+      t.vfo_pitch = b->vfo_pitch;
+      t.vfo_base = g.base;
+      t.vfo_count = g.count;
+      t.n_mid = g.n_mid;
+      t.z0_end = head / 32;
+      t.z1_lo = fix_at >= 0 ? fix_at / 32 : 0;
+      t.z1_hi = fix_at >= 0 ? std::min((fix_at + zone) / 32, g.n_mid) : 0;
+      // the stage-D rows are single-buffered: the previous block's tail and history shift must be through with them
+      if (k >= 1) CU(cudaStreamWaitEvent(sA, b->ev_post[(k - 1) & 1], 0));
+      ddc_tc_kernel<<<(unsigned)g.tc_grid, kTcThreads, kTcSmem, sA>>>(t);
+      CU(cudaGetLastError());
+      ++launches;
     } else {
       CU(cudaMemsetAsync(g.d_sched, 0, sizeof(int) * g.sched_words, sA));
       dim3 grid((unsigned)(p.ngroups + g.nparts));
       CU(launch_main(fmt_in, g.DA, p, grid, sA, fast));
       ++launches;
     }
-    if (b->nested && !g.direct) { const int rc = launch_deep(g, sA); if (rc != AERODDC_OK) return rc; }
+    if (b->nested && !g.direct && g.tc_ntiles == 0) { const int rc = launch_deep(g, sA); if (rc != AERODDC_OK) return rc; }
   }
   CU(cudaEventRecord(b->ev_m1[slot], sA));
   if (!b->nested) {
     CU(cudaEventRecord(b->ev_main[par], sA));
     CU(cudaStreamWaitEvent(sB, b->ev_main[par], 0));
     CU(cudaMemsetAsync(b->d_post_ctr, 0, sizeof(int) * (1 + b->groups.size()), sB));
-    for (const Group& g : b->groups) { const int rc = launch_deep(g, sB); if (rc != AERODDC_OK) return rc; }
+    for (const Group& g : b->groups) if (g.tc_ntiles == 0) { const int rc = launch_deep(g, sB); if (rc != AERODDC_OK) return rc; }
   }
   {
     // payload rows are double-buffered by block parity; wait until the copy-out of this parity (two blocks ago) is done
@@ -422,6 +429,7 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
     CU(cudaGetLastError());
     ++launches;
   }
+  CU(cudaEventRecord(b->ev_post[par], sB));
   // payloads leave on their own stream, overlapping the next block's kernels
   CU(cudaStreamWaitEvent(b->s_d2h, b->ev_tail[par], 0));
   CU(cudaMemcpyAsync(b->h_out[slot], b->d_out + (size_t)par * b->out_total, b->out_total, cudaMemcpyDeviceToHost, b->s_d2h));
@@ -797,6 +805,7 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
     CU(cudaEventCreateWithFlags(&b->ev_tail[i], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&b->ev_d2h[i], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&b->ev_main[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&b->ev_post[i], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&b->ev_dcc[i], cudaEventDisableTiming));
   }
   // every instance of the main kernel may be launched by this bank: raise their dynamic shared-memory limits once
@@ -829,26 +838,52 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
     for (Group& g : b->groups) {
       if (g.parent >= 0 || g.DA != kFastStages || g.direct) continue;          // raw-fed groups with deep stages only
       if (!(b->fmt == AERODDC_CF32 || b->dcc)) continue;                       // the X tiles are staged from cf32
-      if (g.blk_in < 4 * kTcHead * 32) continue;
+      if (g.blk_in < 8 * kTcHead * 32 || g.n_mid % 32) continue;                // short or ragged blocks: not worth it
       if (!d_g) {
         CU(cudaMalloc((void**)&d_g, sizeof(double) * kTcTaps));
         CU(cudaMemcpy(d_g, g5.data(), sizeof(double) * kTcTaps, cudaMemcpyHostToDevice));
       }
       g.tc_ntiles = (g.count + kTcVfos - 1) / kTcVfos;
       CU(dmalloc((void**)&g.d_filt, (size_t)g.tc_ntiles * kTcKSteps * kTcFSlab));
-      const int n = g.tc_ntiles * kTcKSteps * kTcN;
+      const int n = g.tc_ntiles * kTcKSteps * kTcRails;
       tc_build_filters_kernel<<<(n + 127) / 128, 128, 0, b->s_compute>>>(b->d_rot, d_g, g.base, g.count, g.tc_ntiles, g.d_filt);
       CU(cudaGetLastError());
+      // one contiguous stretch of the (VFO tile, time) plane per CTA, cut at multiples of 256 outputs and at tile ends
+      const long long U = (long long)g.tc_ntiles * g.n_mid;
+      const int P = (int)std::max<long long>(1, std::min<long long>(b->n_sm, U / 1024));
+      auto bound = [&](int c) -> long long {
+        if (c >= P) return U;
+        const long long gg = U * c / P;
+        return gg / g.n_mid * g.n_mid + (gg % g.n_mid) / kTcCols * kTcCols;
+      };
+      std::vector<TcSeg> segs;
+      std::vector<int> cta_seg(P + 1, 0);
+      for (int c = 0; c < P; ++c) {
+        cta_seg[c] = (int)segs.size();
+        long long gg = bound(c);
+        const long long g1 = bound(c + 1);
+        while (gg < g1) {
+          TcSeg sg;
+          sg.nt = (int)(gg / g.n_mid);
+          sg.m_lo = (int)(gg % g.n_mid);
+          sg.m_hi = (int)std::min<long long>(g.n_mid, sg.m_lo + (g1 - gg));
+          segs.push_back(sg);
+          gg += sg.m_hi - sg.m_lo;
+        }
+      }
+      cta_seg[P] = (int)segs.size();
+      g.tc_grid = P;
+      CU(dmalloc((void**)&g.d_segs, sizeof(TcSeg) * segs.size()));
+      CU(cudaMemcpy(g.d_segs, segs.data(), sizeof(TcSeg) * segs.size(), cudaMemcpyHostToDevice));
+      CU(dmalloc((void**)&g.d_cta_seg, sizeof(int) * cta_seg.size()));
+      CU(cudaMemcpy(g.d_cta_seg, cta_seg.data(), sizeof(int) * cta_seg.size(), cudaMemcpyHostToDevice));
       any = true;
     }
     if (any) {
       CU(dmalloc((void**)&b->d_pw, sizeof(float2) * (size_t)kTcPwRows * b->vfo_pitch));
       tc_build_pw_kernel<<<dim3((b->vfo_pitch + 127) / 128, kTcPwRows), 128, 0, b->s_compute>>>(b->d_rot, b->vfo_pitch, b->d_pw);
       CU(cudaGetLastError());
-      const char* env_fs = getenv("AERODDC_TC_FSTAGES");   // experiments: depth of the filter-slab ring (6 or 9)
-      b->tc_fstages = env_fs && atoi(env_fs) == 6 ? 6 : 9;
-      CU(cudaFuncSetAttribute(ddc_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<6>::kTotal));
-      CU(cudaFuncSetAttribute(ddc_tc_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<9>::kTotal));
+      CU(cudaFuncSetAttribute(ddc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
       CU(cudaStreamSynchronize(b->s_compute));
     }
     if (d_g) cudaFree(d_g);

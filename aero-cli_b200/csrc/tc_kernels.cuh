@@ -1,8 +1,9 @@
-// aero-ddc-b200: tensor-core formulation of the NCO mix + the first five half-band stages (AERODDC_MODE_TENSOR).
+// aero-ddc-b200: tensor-core formulation of the NCO mix + the first five half-band stages (AERODDC_MODE_TENSOR),
+// with the remaining half-band stages fused into the epilogue.
 //
-// Same path as ddc_main_kernel (vfo.cpp:155-161 mix, halfbanddecimator.cpp:35-60 x 5), recast as the complex GEMM
-// north_star names. NOT bit-identical: a tolerance mode (max |err| <= 1e-4 FS, error SNR >= 80 dB), checked against
-// the exact mode in tests/test_gpu_parity.py and by decoded-frame identity.
+// Same path as ddc_main_kernel + ddc_deep_kernel (vfo.cpp:155-161 mix, halfbanddecimator.cpp:35-60 x D), recast as the
+// complex GEMM north_star names. NOT bit-identical: a tolerance mode (max |err| <= 1e-4 FS, error SNR >= 80 dB), checked
+// against the exact mode in tests/test_gpu_parity.py and by decoded-frame identity.
 //
 // Algebra (scratch/tc_model.py checks it on the CPU). Five cascaded 11-tap half-band decimators are one 311-tap FIR g
 // decimating by 32: z[m] = sum_t g[t] q[n_s + t] x[n_s + t], n_s = 32 m - 310. The reference oscillator q is a
@@ -12,21 +13,27 @@
 // followed by ONE complex multiply per output with the exact recurrence value q[n_s] (exact checkpoint x rotation).
 // q[n_s] restarts from (1, 0) with an amplitude transient at every table wrap and the half-band queues are re-seeded
 // with a one-sample shift at every block start (dsp.cpp:163-172): windows touching either are not a clean FIR and
-// stay on the FP32 kernel (the head of every block and the zone after a wrap; see bank.cu).
+// stay on the FP32 kernel (the head of every block and the zone after a wrap; bank.cu launches it over those
+// stretches first and this kernel picks its stage-5 samples up from the `zone` stream).
 //
 // GEMM shape. Windows are padded to 320 samples starting at 32 m - 312 (a multiple of 8). Rows of X are the block cut
-// into 32-sample rows (64 floats re/im interleaved); output m needs rows m-10 .. m. D[m][n] = sum over 40 k-steps of
-// 8 samples (K = 16 bf16) of X[m + j][chunk] * F[n][k-step], n = (VFO, rail): rail 0 taps (Gr, -Gi), rail 1 (Gi, Gr).
-// A operand = X tile in shared memory, K-major, no swizzle, laid out [16-byte chunk][row][16 B]: rows are 16 bytes
-// apart, so the j-row shift of a k-step is just a start-address offset of the matrix descriptor - every raw sample is
-// staged ONCE per tile instead of ten times (no im2col). B operand = the filter slab of the k-step, streamed from L2
-// with bulk copies. Accumulators: M=128 outputs x N=256 rails fp32 in TMEM, double-buffered (512 columns).
+// into 32-sample rows (64 floats re/im interleaved); output m needs rows m-10 .. m.
+//   D[rail][m] = sum over 40 k-steps of 8 samples (K = 16 bf16) of F[rail][k-step] * X[m + j][chunk]
+// rail = (VFO, re/im): rail 0 taps (Gr, -Gi), rail 1 (Gi, Gr). A operand = the filter slab of the k-step (128 rails = 64
+// VFOs), streamed from L2 with bulk copies. B operand = X tile in shared memory, K-major, no swizzle, laid out
+// [16-byte chunk][row][16 B]: rows are 16 bytes apart, so the j-row shift of a k-step is just a start-address offset of
+// the matrix descriptor - every raw sample is staged ONCE per tile instead of ten times (no im2col). Accumulators:
+// M=128 rails x N=256 outputs fp32 in TMEM, double-buffered (512 columns). With rails on the TMEM lanes, an epilogue
+// thread owns ONE rail and reads its time series along the columns: it rotates by q (partner rail by shuffle), then
+// runs the remaining D-5 half-band stages on its rail in registers (the half-band taps are real, so the rails are
+// independent) and writes stage-D samples. No intermediate stream, no second kernel.
 // Precision: operands are split in bf16 hi + mid (x = hi + mid + O(2^-17 x)); three products hi*hi + mid*hi + hi*mid
 // per k-step (the dropped terms are ~2^-17 relative: 107 dB SNR in the model), fp32 accumulation.
 //
-// Warp roles (320 threads, one CTA per SM, persistent over tiles): warps 0-3 epilogue (TMEM -> registers -> rotate ->
-// stage-5 stream), warps 4-7 stage X (global -> bf16 hi/mid -> shared), warp 8 streams filter slabs (bulk copy),
-// warp 9 issues tcgen05.mma.
+// Work split: the (VFO tile, time) plane is cut on the host into one contiguous stretch per CTA (equal work, one wave
+// of persistent CTAs); a stretch that does not begin at a block start runs the fused stages in over 96 stage-5 samples.
+// Warp roles (320 threads, one CTA per SM): warps 0-3 epilogue, warps 4-7 stage X (global -> bf16 hi/mid -> shared),
+// warp 8 streams filter slabs (bulk copy), warp 9 issues tcgen05.mma.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -34,39 +41,47 @@
 
 namespace aeroddc {
 
-constexpr int kTcM = 128;                 // outputs (stage-5 samples) per tile
-constexpr int kTcN = 256;                 // rails per tile
-constexpr int kTcVfos = kTcN / 2;         // VFOs per tile
+constexpr int kTcRails = 128;             // rails per tile (MMA M)
+constexpr int kTcVfos = kTcRails / 2;     // VFOs per tile
+constexpr int kTcCols = 256;              // outputs (stage-5 samples) per tile (MMA N)
 constexpr int kTcTaps = 311;              // 1 + 10 * (2^5 - 1)
 constexpr int kTcWin = 320;               // padded window, samples
 constexpr int kTcLead = 312;              // window start = 32 m - kTcLead
 constexpr int kTcKSteps = kTcWin / 8;     // 40 MMA k-steps of 8 samples
 constexpr int kTcBack = 10;               // rows before the output's own row
-constexpr int kTcRows = 144;              // rows per X tile (138 used)
+constexpr int kTcRows = 272;              // rows per X tile (266 used)
 constexpr int kTcXPart = 8 * kTcRows * 16;            // one bf16 part of an X tile: [8 chunks][rows][16 B]
 constexpr int kTcXStage = 2 * kTcXPart;               // hi | mid
 constexpr int kTcXStages = 2;
-constexpr int kTcFPart = 2 * kTcN * 16;               // one bf16 part of a filter slab: [2 chunks][256 rails][16 B]
+constexpr int kTcFPart = 2 * kTcRails * 16;           // one bf16 part of a filter slab: [2 chunks][128 rails][16 B]
 constexpr int kTcFSlab = 2 * kTcFPart;                // hi | mid
-template <int FS> struct TcSmem {   // FS = filter-slab ring depth
-  static constexpr int kBars = 2 * kTcXStages + 2 * FS + 4;
-  static constexpr int kTotal = kTcXStages * kTcXStage + FS * kTcFSlab + 8 * kBars + 16;
-};
+constexpr int kTcFStages = 6;
+constexpr int kTcBars = 2 * kTcXStages + 2 * kTcFStages + 4;
+constexpr int kTcSmem = kTcXStages * kTcXStage + kTcFStages * kTcFSlab + 8 * kTcBars + 16;
 constexpr int kTcThreads = 320;
 constexpr int kTcPwRows = 512;            // rotation table rows: u^r, r = 0 .. 511
 constexpr int kTcHead = 64;               // outputs [0, kTcHead) of a block (2048 samples) stay on the FP32 kernel
+constexpr int kTcRunIn = 96;              // stage-5 samples of run-in for the fused stages (10 * (2^3 - 1), rounded to 32)
+
+struct TcSeg { int nt, m_lo, m_hi; };     // a stretch of one VFO tile: stage-5 outputs [m_lo, m_hi), multiples of 32
 
 struct TcParams {
   RawBlock raw;               // the block (cf32), possibly in slices on several GPUs (a 32-sample row never straddles slices)
   const uint4* filt;          // [n_ntiles][kTcKSteps][kTcFSlab / 16]
   const float2* ckpt;         // [nck][vfo_pitch] exact NCO checkpoints (state after 256 k steps)
   const float2* pw;           // [kTcPwRows][vfo_pitch] u^r
-  float2* mid;                // [32-VFO group][n_mid][32] stage-5 stream of this block
+  const float2* zone;         // [32-VFO group][n_mid][32] stage-5 samples the FP32 kernel computed for the zones
+  const float2* state_in;     // [kMaxStages][kStateSlots][vfo_pitch] block-start history (stages 5.. are used here)
+  float2* state_out;
+  float2* const* xd_rows;     // [vfo_pitch] per VFO: where stage-D sample 0 of this block goes
+  const unsigned char* vfo_D; // [vfo_pitch]
+  const TcSeg* segs;          // host-planned stretches
+  const int* cta_seg;         // [gridDim.x + 1] stretches of CTA c: [cta_seg[c], cta_seg[c + 1])
   long long block_abs;
-  int nco_len, nck, vfo_pitch, vfo_base, vfo_count, mid_groups;
+  int nco_len, nck, vfo_pitch, vfo_base, vfo_count;
   int n_mid;                  // B / 32
-  int m_first, m_end;         // outputs [m_first, m_end)
-  int n_ntiles, n_mtiles;
+  int z0_end;                 // zone 0 = outputs [0, z0_end)
+  int z1_lo, z1_hi;           // zone 1 = outputs [z1_lo, z1_hi) (empty when z1_hi == 0)
 };
 
 // ---- tcgen05 helpers ----
@@ -84,22 +99,22 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, 
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
 // kind::f16, A = B = bf16 (K-major), D = f32, M = 128, N = 256 (InstrDescriptor bit layout of the same header)
-constexpr uint32_t kTcIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+constexpr uint32_t kTcIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcCols >> 3) << 17) | ((uint32_t)(kTcRails >> 4) << 24);
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a), "l"(b), "r"(kTcIdesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),
+        "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]),
+        "=f"(r[16]), "=f"(r[17]), "=f"(r[18]), "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]),
+        "=f"(r[24]), "=f"(r[25]), "=f"(r[26]), "=f"(r[27]), "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31])
       : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -113,9 +128,48 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   mid = *reinterpret_cast<const uint32_t*>(&m);
 }
 
-template <int kTcFStages>
+// One rail of one half-band stage, fused arithmetic (the tolerance modes' hb_out_fast, one lane of it).
+// e[k] = x[2(j-5+k)], o[k] = x[2(j-3+k)+1], ox = the three odd-phase samples before o[0] (for the block-end history).
+struct RailHb { float e[5], o[3], ox[3]; };
+__device__ __forceinline__ float rail_pair(RailHb& h, float xe, float xo) {
+  const float s0 = h.e[0] + xe, s2 = h.e[1] + h.e[4], s4 = h.e[2] + h.e[3];
+  const float y = fmaf(s4, HB_P4, fmaf(h.o[0], HB_P5, fmaf(s2, HB_P2, s0 * HB_P0)));
+  h.ox[0] = h.ox[1]; h.ox[1] = h.ox[2]; h.ox[2] = h.o[0];
+  h.e[0] = h.e[1]; h.e[1] = h.e[2]; h.e[2] = h.e[3]; h.e[3] = h.e[4]; h.e[4] = xe;
+  h.o[0] = h.o[1]; h.o[1] = h.o[2]; h.o[2] = xo;
+  return y;
+}
+
+// the tile sequence of this CTA, walked identically by every warp role
+struct TcWalk {
+  const TcSeg* segs;
+  int si, si_end, nt, m_lo, m_hi, m0;
+  bool seg_first;   // m0 is the first tile of its stretch
+  __device__ __forceinline__ void open() {
+    const TcSeg s = segs[si];
+    nt = s.nt; m_lo = s.m_lo; m_hi = s.m_hi;
+    m0 = m_lo > 0 ? m_lo - kTcRunIn : 0;
+    seg_first = true;
+  }
+  __device__ __forceinline__ bool start(const TcParams& p) {
+    segs = p.segs;
+    si = p.cta_seg[blockIdx.x];
+    si_end = p.cta_seg[blockIdx.x + 1];
+    if (si >= si_end) return false;
+    open();
+    return true;
+  }
+  __device__ __forceinline__ bool next() {
+    m0 += kTcCols;
+    seg_first = false;
+    if (m0 < m_hi) return true;
+    if (++si >= si_end) return false;
+    open();
+    return true;
+  }
+};
+
 __global__ void __launch_bounds__(kTcThreads, 1) ddc_tc_kernel(const TcParams p) {
-  constexpr int kTcBars = TcSmem<kTcFStages>::kBars;
   extern __shared__ __align__(1024) unsigned char tsm[];
   unsigned char* xs = tsm;
   unsigned char* fsl = tsm + kTcXStages * kTcXStage;
@@ -143,66 +197,138 @@ __global__ void __launch_bounds__(kTcThreads, 1) ddc_tc_kernel(const TcParams p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int ntiles = p.n_ntiles * p.n_mtiles;
+  TcWalk w;
+  const bool any = w.start(p);
 
   if (warp < 4) {
-    // ===== epilogue: D (TMEM) x q[n_s] -> stage-5 stream =====
+    // ===== epilogue: one rail per thread: D (TMEM) x q[n_s] -> fused half-band stages -> stage-D rows =====
+    const int rail = lane & 1;
+    int slot = 0, col = 0, nd = 0;
+    bool active = false;
+    float2* xd = nullptr;
+    RailHb hb[kDeepStages];
     int tl = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
+    if (any) do {
       const int a = tl & 1;
-      const int nt = t / p.n_mtiles, mt = t - nt * p.n_mtiles;
-      const int m = p.m_first + mt * kTcM + warp * 32 + lane;
+      if (w.seg_first) {
+        slot = w.nt * kTcVfos + warp * 16 + (lane >> 1);
+        active = slot < p.vfo_count;
+        col = min(p.vfo_base + slot, p.vfo_pitch - 1);
+        nd = max((int)p.vfo_D[col] - kFastStages, 0);
+        xd = p.xd_rows[col];
+#pragma unroll
+        for (int s = 0; s < kDeepStages; ++s) {
+#pragma unroll
+          for (int k = 0; k < 5; ++k) hb[s].e[k] = 0.f;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { hb[s].o[k] = 0.f; hb[s].ox[k] = 0.f; }
+          if (w.m_lo == 0 && s < nd) {   // block start: the saved (shifted) history of this stage, this rail
+            const float2* st = p.state_in + (size_t)(kFastStages + s) * kStateSlots * p.vfo_pitch + col;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) { const float2 v = st[(size_t)k * p.vfo_pitch]; hb[s].e[k] = rail ? v.y : v.x; }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { const float2 v = st[(size_t)(5 + k) * p.vfo_pitch]; hb[s].o[k] = rail ? v.y : v.x; }
+          }
+        }
+      }
       mbar_wait(&tfull[a], (tl >> 1) & 1);
       tc_fence_after();
-      // the oscillator value the window's first sample is mixed with: S(idx + 1) = ckpt[c] * u^r
-      const long long n_s = p.block_abs + 32ll * m - kTcLead;
-      const int idx1 = (int)(n_s % p.nco_len) + 1;
-      const int c = min(idx1 >> 8, p.nck - 1);
-      const int r = idx1 - (c << 8);
-      const float2* ck_row = p.ckpt + (size_t)c * p.vfo_pitch;
-      const float2* pw_row = p.pw + (size_t)r * p.vfo_pitch;
+      const float2* ck_col = p.ckpt + col;
+      const float2* pw_col = p.pw + col;
+      const float2* zone_col = p.zone + (size_t)(slot >> 5) * p.n_mid * 32 + (slot & 31);
 #pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        const int slot0 = nt * kTcVfos + q * 32;          // first VFO slot (within the launch group) of this 32-group
-        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * kTcN + q * 64);
-        uint32_t d0[32], d1[32];
-        tc_ld32(taddr, d0);
-        tc_ld32(taddr + 32, d1);
+      for (int cb = 0; cb < kTcCols; cb += 32) {
+        const int mc = w.m0 + cb;                  // 32 consecutive stage-5 outputs, mc a multiple of 32
+        if (mc >= w.m_hi) break;                   // uniform: nothing of this stretch beyond
+        float d[32];
+        tc_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * kTcCols + cb), d);
         tc_ld_wait();
-        if (slot0 < p.mid_groups * 32 && m < p.m_end) {
-          float4* out = reinterpret_cast<float4*>(p.mid + ((size_t)(slot0 >> 5) * p.n_mid + m) * 32);
+        // q for output mc + i: the oscillator state after idx1 + 32 i steps, idx1 = table index of the window's first sample
+        // plus one: exact checkpoint (every 256 steps) times the unit rotation over the remainder. The remainder cycles
+        // through 8 values per 32 outputs and the checkpoint row advances every 8 outputs. (Indices past the table end
+        // only occur in the zones, whose outputs are replaced below: clamped, never wrapped.)
+        long long n_s = (p.block_abs + 32ll * mc - kTcLead) % p.nco_len;
+        if (n_s < 0) n_s += p.nco_len;
+        const int idx1 = (int)n_s + 1;
+        const int c0 = idx1 >> 8, r0 = idx1 & 255;
+        const int kc = (256 - r0 + 31) >> 5;        // outputs i with (i & 7) >= kc use the next checkpoint row
+        float2 pwk[8], ckc[5];
 #pragma unroll
-          for (int v = 0; v < 32; v += 2) {
-            float z[4];
+        for (int k = 0; k < 8; ++k) pwk[k] = __ldg(pw_col + (size_t)((r0 + 32 * k) & 255) * p.vfo_pitch);
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int col = min(p.vfo_base + slot0 + v + e, p.vfo_pitch - 1);
-              const float2 ck = __ldg(ck_row + col), pw = __ldg(pw_row + col);
-              const float fr = ck.x * pw.x - ck.y * pw.y, fi = ck.x * pw.y + ck.y * pw.x;
-              const int w = 2 * (v + e);
-              const float dr = __uint_as_float(w < 32 ? d0[w & 31] : d1[w & 31]);
-              const float di = __uint_as_float(w < 32 ? d0[(w + 1) & 31] : d1[(w + 1) & 31]);
-              z[2 * e] = dr * fr - di * fi;
-              z[2 * e + 1] = dr * fi + di * fr;
-            }
-            out[v >> 1] = make_float4(z[0], z[1], z[2], z[3]);
+        for (int j = 0; j < 5; ++j) ckc[j] = __ldg(ck_col + (size_t)min(c0 + j, p.nck - 1) * p.vfo_pitch);
+        const bool in_zone = mc < p.z0_end || (mc < p.z1_hi && mc + 32 > p.z1_lo);
+        float z[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const bool up = (i & 7) >= kc;
+          const float cx = up ? ckc[(i >> 3) + 1].x : ckc[i >> 3].x, cy = up ? ckc[(i >> 3) + 1].y : ckc[i >> 3].y;
+          const float2 pw = pwk[i & 7];
+          const float fr = cx * pw.x - cy * pw.y, fi = cx * pw.y + cy * pw.x;
+          const float own = d[i], oth = __shfl_xor_sync(0xffffffffu, own, 1);
+          // rail 0: dr fr - di fi (own = dr); rail 1: dr fi + di fr (own = di)
+          z[i] = fmaf(own, fr, oth * (rail ? fi : -fi));
+        }
+        if (in_zone) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int m = mc + i;
+            if (m < p.z0_end || (m >= p.z1_lo && m < p.z1_hi)) { const float2 v = zone_col[(size_t)m * 32]; z[i] = rail ? v.y : v.x; }
           }
+        }
+        // fused half-band stages on this rail: 32 -> 16 -> 8 -> 4
+        float y0[16], y1[8], y2[4];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) y0[j] = rail_pair(hb[0], z[2 * j], z[2 * j + 1]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y1[j] = rail_pair(hb[1], y0[2 * j], y0[2 * j + 1]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y2[j] = rail_pair(hb[2], y1[2 * j], y1[2 * j + 1]);
+        const bool keep = mc >= w.m_lo;            // run-in outputs are dropped (m_lo is a multiple of 32)
+        // the even lane of a pair writes (re, im); lanes of a warp may differ in their stage count
+        const bool wr = keep && active && rail == 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float o = __shfl_xor_sync(0xffffffffu, y2[j], 1); if (wr && nd == 3) xd[(mc >> 3) + j] = make_float2(y2[j], o); }
+        if (__any_sync(0xffffffffu, nd < 3)) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float o = __shfl_xor_sync(0xffffffffu, y1[j], 1); if (wr && nd == 2) xd[(mc >> 2) + j] = make_float2(y1[j], o); }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { const float o = __shfl_xor_sync(0xffffffffu, y0[j], 1); if (wr && nd == 1) xd[(mc >> 1) + j] = make_float2(y0[j], o); }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { const float o = __shfl_xor_sync(0xffffffffu, z[j], 1); if (wr && nd == 0) xd[mc + j] = make_float2(z[j], o); }
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty[a]);
-    }
+      // end of the block's stream: the shifted history the fused stages start the next block from (see boundary_role)
+      if (w.m0 + kTcCols >= w.m_hi && w.m_hi == p.n_mid && active) {
+#pragma unroll
+        for (int s = 0; s < kDeepStages; ++s) {
+          if (s < nd) {
+            float* st = reinterpret_cast<float*>(p.state_out + (size_t)(kFastStages + s) * kStateSlots * p.vfo_pitch + col) + rail;
+            const size_t pitch = (size_t)p.vfo_pitch * 2;
+            st[0] = hb[s].ox[0];               // x[n-11]
+            st[pitch] = hb[s].ox[1];           // x[n-9]
+            st[2 * pitch] = hb[s].ox[2];       // x[n-7]
+            st[3 * pitch] = hb[s].o[0];        // x[n-5]
+            st[4 * pitch] = hb[s].o[1];        // x[n-3]
+#pragma unroll
+            for (int k = 0; k < 3; ++k) st[(size_t)(5 + k) * pitch] = hb[s].e[2 + k];   // x[n-6], x[n-4], x[n-2]
+          }
+        }
+      }
+      ++tl;
+    } while (w.next());
   } else if (warp < 8) {
     // ===== X producer: rows of the raw block -> bf16 hi / mid, [chunk][row][16 B] =====
     const int ptid = threadIdx.x - 128;
     int tl = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
+    if (any) do {
       const int xsi = tl & 1;
-      const int mt = t % p.n_mtiles;
-      const int row0 = p.m_first + mt * kTcM - kTcBack;
+      const int row0 = w.m0 - kTcBack;
       mbar_wait(&xempty[xsi], ((tl >> 1) & 1) ^ 1);
       unsigned char* hi_base = xs + xsi * kTcXStage;
-      for (int i = ptid; i < kTcM + kTcBack; i += 128) {
+      for (int i = ptid; i < kTcCols + kTcBack; i += 128) {
         const int rho = row0 + i;
         const bool valid = rho >= 0 && rho < p.n_mid;
         const int g0 = (valid ? rho : 0) * 32;
@@ -210,46 +336,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) ddc_tc_kernel(const TcParams p)
         const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(p.raw.slice[sl]) + (g0 - sl * p.raw.slice_len));
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          float4 u = make_float4(0.f, 0.f, 0.f, 0.f), w = u;
-          if (valid) { u = __ldg(src + 2 * c); w = __ldg(src + 2 * c + 1); }
+          float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
+          if (valid) { u = __ldg(src + 2 * c); v = __ldg(src + 2 * c + 1); }
           uint4 h, mdl;
           split_pair(u.x, u.y, h.x, mdl.x);
           split_pair(u.z, u.w, h.y, mdl.y);
-          split_pair(w.x, w.y, h.z, mdl.z);
-          split_pair(w.z, w.w, h.w, mdl.w);
+          split_pair(v.x, v.y, h.z, mdl.z);
+          split_pair(v.z, v.w, h.w, mdl.w);
           *reinterpret_cast<uint4*>(hi_base + (c * kTcRows + i) * 16) = h;
           *reinterpret_cast<uint4*>(hi_base + kTcXPart + (c * kTcRows + i) * 16) = mdl;
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's reads
       mbar_arrive(&xfull[xsi]);
-    }
+      ++tl;
+    } while (w.next());
   } else if (warp == 8) {
-    // ===== filter slabs: one 16 KB bulk copy per k-step =====
-    if (lane == 0) {
+    // ===== filter slabs: one 8 KB bulk copy per k-step =====
+    if (lane == 0 && any) {
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int nt = t / p.n_mtiles;
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.filt) + (size_t)nt * kTcKSteps * kTcFSlab;
+      do {
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.filt) + (size_t)w.nt * kTcKSteps * kTcFSlab;
         for (int ks = 0; ks < kTcKSteps; ++ks, ++it) {
           const int fsi = it % kTcFStages;
           mbar_wait(&fempty[fsi], ((it / kTcFStages) & 1) ^ 1);
           mbar_expect_tx(&ffull[fsi], kTcFSlab);
           tma_bulk_g2s(fsl + fsi * kTcFSlab, src + (size_t)ks * kTcFSlab, kTcFSlab, &ffull[fsi]);
         }
-      }
+      } while (w.next());
     }
   } else {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (lane == 0 && any) {
       uint32_t it = 0;
       int tl = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
+      do {
         const int a = tl & 1, xsi = tl & 1;
         mbar_wait(&tempty[a], ((tl >> 1) & 1) ^ 1);
         mbar_wait(&xfull[xsi], (tl >> 1) & 1);
         tc_fence_after();
-        const uint32_t d = tmem + (uint32_t)(a * kTcN);
+        const uint32_t d = tmem + (uint32_t)(a * kTcCols);
         const uint32_t xhi = smem_u32(xs + xsi * kTcXStage), xmid = xhi + kTcXPart;
         for (int ks = 0; ks < kTcKSteps; ++ks, ++it) {
           const int fsi = it % kTcFStages;
@@ -257,17 +383,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) ddc_tc_kernel(const TcParams p)
           tc_fence_after();
           const int s = 8 + 8 * ks;                       // first sample of the k-step, counted from row (m - 10)
           const uint32_t xo = (uint32_t)((((s & 31) >> 2) * kTcRows + (s >> 5)) * 16);
-          const uint64_t ah = tc_desc(xhi + xo, kTcRows * 16, 128), am = tc_desc(xmid + xo, kTcRows * 16, 128);
+          const uint64_t bh = tc_desc(xhi + xo, kTcRows * 16, 128), bm = tc_desc(xmid + xo, kTcRows * 16, 128);
           const uint32_t fb = smem_u32(fsl + fsi * kTcFSlab);
-          const uint64_t bh = tc_desc(fb, kTcN * 16, 128), bm = tc_desc(fb + kTcFPart, kTcN * 16, 128);
+          const uint64_t ah = tc_desc(fb, kTcRails * 16, 128), am = tc_desc(fb + kTcFPart, kTcRails * 16, 128);
           tc_mma(d, ah, bh, ks > 0);
-          tc_mma(d, am, bh, 1);
           tc_mma(d, ah, bm, 1);
+          tc_mma(d, am, bh, 1);
           tc_commit(&fempty[fsi]);
         }
         tc_commit(&xempty[xsi]);
         tc_commit(&tfull[a]);
-      }
+        ++tl;
+      } while (w.next());
     }
   }
   tc_fence_before();
@@ -276,13 +403,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) ddc_tc_kernel(const TcParams p)
 }
 
 // ---- finalize-time tables ----
-// filt[nt][ks][part][chunk][n][8 bf16]: n = 2 * (VFO within the tile) + rail; element k of the k-step: sample 8 ks + k / 2
-// of the padded window, component k & 1. Rail 0 (real): (Gr, -Gi); rail 1 (imaginary): (Gi, Gr); G = g[t' - 2] u^t'.
+// filt[nt][ks][part][chunk][rail][8 bf16]: rail = 2 * (VFO within the tile) + re/im; element k of the k-step: sample
+// 8 ks + k / 2 of the padded window, component k & 1. Rail 0 (real): (Gr, -Gi); rail 1 (imaginary): (Gi, Gr);
+// G = g[t' - 2] u^t'.
 __global__ void tc_build_filters_kernel(const float2* __restrict__ rot, const double* __restrict__ g, int vfo_base, int vfo_count,
                                         int n_ntiles, uint4* __restrict__ filt) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;   // over n_ntiles * kTcKSteps * kTcN
-  if (n >= n_ntiles * kTcKSteps * kTcN) return;
-  const int rail_n = n % kTcN, ks = (n / kTcN) % kTcKSteps, nt = n / (kTcN * kTcKSteps);
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;   // over n_ntiles * kTcKSteps * kTcRails
+  if (n >= n_ntiles * kTcKSteps * kTcRails) return;
+  const int rail_n = n % kTcRails, ks = (n / kTcRails) % kTcKSteps, nt = n / (kTcRails * kTcKSteps);
   const int slot = nt * kTcVfos + (rail_n >> 1), rail = rail_n & 1;
   float val[16];
 #pragma unroll
@@ -305,8 +433,8 @@ __global__ void tc_build_filters_kernel(const float2* __restrict__ rot, const do
   uint4* slab = filt + (size_t)(nt * kTcKSteps + ks) * (kTcFSlab / 16);
 #pragma unroll
   for (int ch = 0; ch < 2; ++ch) {
-    slab[ch * kTcN + rail_n] = make_uint4(hi[4 * ch], hi[4 * ch + 1], hi[4 * ch + 2], hi[4 * ch + 3]);
-    slab[(kTcFPart / 16) + ch * kTcN + rail_n] = make_uint4(mid[4 * ch], mid[4 * ch + 1], mid[4 * ch + 2], mid[4 * ch + 3]);
+    slab[ch * kTcRails + rail_n] = make_uint4(hi[4 * ch], hi[4 * ch + 1], hi[4 * ch + 2], hi[4 * ch + 3]);
+    slab[(kTcFPart / 16) + ch * kTcRails + rail_n] = make_uint4(mid[4 * ch], mid[4 * ch + 1], mid[4 * ch + 2], mid[4 * ch + 3]);
   }
 }
 

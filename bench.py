@@ -786,8 +786,7 @@ def main():
             "wall_ms_per_step": wall_ms / args.steps,
         }
         if tens:
-            mma_flop = 3 * 2.0 * 256 * 128 * 640            # three bf16 products per k-step, M=128 x N=256 x K=640 per tile
-            tiles = -(-len(mine) // 128) * -(-((BLOCK >> 5) - 64) // 128)
+            mma_flops = 3 * 2.0 * (2 * len(mine)) * (BLOCK >> 5) * 640   # three bf16 products x (rails x stage-5 outputs x K = 640) per launch
             tol = tens["tol"]
             bf16_peak = None
             if os.path.exists(mp):
@@ -798,9 +797,9 @@ def main():
                         "d2h_bytes_per_step": int(args.vfos * (BLOCK >> DECIM) // LATE * 2)},
                 "realtime_x": total / (tens["ms"] * 1e-3) / (args.vfos * FS),
                 "main_ms": tens["main_ms"], "launches_per_step": tens["launches"],
-                "roofline": {"bound": "tensor", "kernel": "ddc_tc_kernel (+ the FP32 head launch)", "unit": "TFLOP/s",
-                             "achieved": tiles * mma_flop / (tens["main_ms"] * 1e-3) / 1e12, "peak": bf16_peak,
-                             "frac": (tiles * mma_flop / (tens["main_ms"] * 1e-3) / 1e12 / bf16_peak) if bf16_peak else None,
+                "roofline": {"bound": "tensor", "kernel": "ddc_tc_kernel (+ the FP32 launch over the block head)", "unit": "TFLOP/s",
+                             "achieved": mma_flops / (tens["main_ms"] * 1e-3) / 1e12, "peak": bf16_peak,
+                             "frac": (mma_flops / (tens["main_ms"] * 1e-3) / 1e12 / bf16_peak) if bf16_peak else None,
                              "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, back to back)",
                              "note": "achieved = bf16 MMA flops issued (3 products of the hi+mid operand split, K padded 311 -> 320 taps) / time of the "
                                      "main-stream kernels of a step; the path's algorithmic work is %.1f flop per VFO-sample (FP32 formulation)" % FLOPS_MAIN},
@@ -809,7 +808,7 @@ def main():
                     "int16_max_abs_err_fs": tol["max_abs_err_lsb"] / 32768.0,
                     "int16_err_snr_db": float(10 * np.log10(tol["ref_power"] / max(tol["err_power"], 1e-30))),
                     "bound": "max|err| <= 1e-4 FS (3.3 LSB), SNR >= 80 dB (BASELINE.json north_star)"},
-                "note": "AERODDC_MODE_TENSOR: NCO mix + half-band stages 0-4 as one complex GEMM on tcgen05 (bf16 hi+mid operand split, fp32 TMEM accumulators); block heads and "
+                "note": "AERODDC_MODE_TENSOR: NCO mix + half-band stages 0-4 as one complex GEMM on tcgen05 (bf16 hi+mid operand split, fp32 TMEM accumulators), stages 5-7 fused into its epilogue; block heads and "
                         "oscillator-restart zones on the FP32 kernel; NOT bit-identical - tolerance mode, decoded frames identical (tests/test_e2e_decode.py); the headline value is the byte-identical mode"}
         if dcc_ms is not None:
             line["dc_correction"] = {"value": float(args.vfos) * BLOCK / (dcc_ms * 1e-3) / 1e9, "unit": "Gsps", "ms_per_step": dcc_ms,
