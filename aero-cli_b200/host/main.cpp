@@ -116,7 +116,7 @@ int main(int argc, char** argv) {
     else if (a == "--zmq-selftest" && i + 1 < argc) zmq_addr = argv[++i];
     else if (a == "-v" || a == "--verbose") {}
     else if (a == "-h" || a == "--help") {
-      printf("usage: aero-publish-b200 -d <file=path,format=cu8|cs16|cf32[,repeat=N] | synthetic=seed[,format=..][,blocks=N]>[,throttle=X][,delay=S][,gpus=N][,mode=fast] [--enable-dcc] [--hash|--dump DIR] <settings.ini>\n"
+      printf("usage: aero-publish-b200 -d <file=path,format=cu8|cs16|cf32[,repeat=N] | synthetic=seed[,format=..][,blocks=N]>[,throttle=X][,delay=S][,gpus=N][,mode=fast|tensor] [--enable-dcc] [--hash|--dump DIR] <settings.ini>\n"
              "       aero-publish-b200 --plan <settings.ini>\n");
       return 0;
     } else ini = a;

@@ -40,6 +40,9 @@ Publisher::Publisher(const std::string& deviceStr, bool enableBiast_, bool enabl
     // "mode=fast" in the device string selects the tolerance mode (fused arithmetic, not bit-identical; include/aeroddc.h)
     if (deviceStr.find("mode=fast") != std::string::npos && aeroddc_fleet_set_mode(bank->handle(), AERODDC_MODE_FAST) != AERODDC_OK)
       throw std::runtime_error(aeroddc_last_error());
+    // "mode=tensor": the tensor-core formulation (same tolerance class; raw-fed VFOs with decim_count >= 6 on cf32 input)
+    if (deviceStr.find("mode=tensor") != std::string::npos && aeroddc_fleet_set_mode(bank->handle(), AERODDC_MODE_TENSOR) != AERODDC_OK)
+      throw std::runtime_error(aeroddc_last_error());
     if (enableDcc && aeroddc_fleet_set_dc_correction(bank->handle(), 1) != AERODDC_OK) throw std::runtime_error(aeroddc_last_error());   // publisher.cpp:292-296, on the GPU
     for (vfo* m : VFOmain) m->addToBank(bank, -1);
     for (vfo* f : VFOflat) f->addToBank(bank, -1);

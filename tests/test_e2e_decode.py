@@ -85,6 +85,12 @@ def test_a_broken_crc_is_rejected_by_the_reference_decoder():
     assert got == expected_records([msgs[0]]) | {r.replace("QNO=01|REFNO=00", "QNO=03|REFNO=02") for r in expected_records([msgs[2]])}
 
 
+# The tensor mode applies to raw-fed VFOs with at least six half-band stages on cf32 input: three 600 bit/s channels as flat
+# VFOs straight off a 1.536 MS/s cf32 capture (seven stages -> 12 kHz audio).
+TENSOR_SCENARIO = dict(bitrate=600, kind="msk", ini=os.path.join(DATA, "e2e_1536k_flat.ini"), seconds=24, lead=6, messages=2, rate=1536000, format="cf32",
+                       channels={"TCH01": (250000 + 650, 0.20, 1), "TCH02": (-370000 + 1100, 0.15, 2), "TCH03": (501000 + 650, 0.25, 3)})
+
+
 def _make_capture(tmp, sc):
     sent = {}
     carriers = []
@@ -95,14 +101,14 @@ def _make_capture(tmp, sc):
         path = tmp / (topic + ".bits")
         bits.tofile(path)
         carriers.append("--carrier=%d:%d:%s:%g:bits=%s" % (offset, sc["bitrate"], sc["kind"], amp, path))
-    iq = tmp / "cap.cu8"
-    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "synth_iq.py"), str(iq), "--format", "cu8", "--rate", "288000", "--seconds",
+    iq = tmp / ("cap." + sc.get("format", "cu8"))
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "synth_iq.py"), str(iq), "--format", sc.get("format", "cu8"), "--rate", str(sc.get("rate", 288000)), "--seconds",
                     str(sc["seconds"]), "--noise", "0.02"] + carriers, check=True, capture_output=True)
     return iq, sent
 
 
-def _cpu_dump(ini, iq, out):
-    subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "oracle_payloads.py"), ini, str(iq), "cu8", str(out)], check=True, capture_output=True)
+def _cpu_dump(ini, iq, out, fmt="cu8"):
+    subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "oracle_payloads.py"), ini, str(iq), fmt, str(out)], check=True, capture_output=True)
 
 
 def _decode(dump, bitrate):
@@ -168,6 +174,34 @@ def test_tolerance_mode_payloads_decode_to_the_identical_acars_set(tmp_path, nam
         worst = max(worst, int(np.abs(a - b).max()))
         err, sig = float(((a - b) ** 2).sum()), float((b ** 2).sum())
         assert err == 0 or 10 * np.log10(sig / err) >= 80.0, topic      # signals of normal level: the stated SNR bound, unconditionally
+    assert worst <= 3                                                   # 1e-4 of full scale = 3.27 LSB
+    from_gpu = _decode(gpu, sc["bitrate"])
+    from_cpu = _decode(cpu, sc["bitrate"])
+    assert from_gpu == from_cpu
+    for topic, msgs in sent.items():
+        assert set(from_gpu[topic]) == expected_records(msgs), topic
+
+
+@pytest.mark.gpu
+def test_tensor_mode_payloads_decode_to_the_identical_acars_set(tmp_path):
+    """AERODDC_MODE_TENSOR (`mode=tensor`: mix + five half-band stages as a tcgen05 GEMM, later stages fused in its epilogue)
+    on a geometry it applies to, through the unchanged decoder: payloads within the stated tolerance of the CPU chain's
+    (max |err| <= 1e-4 FS, SNR >= 80 dB, unconditionally), identical record lists, and the messages that were sent."""
+    sc = TENSOR_SCENARIO
+    iq, sent = _make_capture(tmp_path, sc)
+    gpu, cpu = tmp_path / "gpu", tmp_path / "cpu"
+    gpu.mkdir()
+    subprocess.run([BIN, "-d", "file=%s,format=cf32,mode=tensor" % iq, "--dump", str(gpu), sc["ini"]], check=True, capture_output=True)
+    _cpu_dump(sc["ini"], iq, cpu, "cf32")
+    worst = 0
+    for topic in sc["channels"]:
+        a = np.fromfile(gpu / (topic + ".i16"), np.int16).astype(np.int32)
+        b = np.fromfile(cpu / (topic + ".i16"), np.int16).astype(np.int32)
+        assert a.size == b.size and a.size > 0
+        assert np.any(a != b)                                           # really the tolerance path, not the exact one
+        worst = max(worst, int(np.abs(a - b).max()))
+        err, sig = float(((a - b) ** 2).sum()), float((b ** 2).sum())
+        assert 10 * np.log10(sig / err) >= 80.0, topic
     assert worst <= 3                                                   # 1e-4 of full scale = 3.27 LSB
     from_gpu = _decode(gpu, sc["bitrate"])
     from_cpu = _decode(cpu, sc["bitrate"])
