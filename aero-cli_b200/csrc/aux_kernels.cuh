@@ -278,28 +278,14 @@ __global__ void __launch_bounds__(32) dcc_kernel(const RawBlock rb, float* __res
   if (lane < 2) state[lane] = a;
 }
 
-// Keep the last `hist` stage-D samples of every VFO in front of its next block: row[i] = row[n_stage + i],
-// i < hist. Source and destination overlap when n_stage < hist; moving forward in chunks with the
-// whole chunk read before any of it is written keeps that safe (dst < src).
-__global__ void __launch_bounds__(256) xd_shift_kernel(const TailVfo* __restrict__ vfos) {
-  const TailVfo v = vfos[blockIdx.x];
+// Keep the last `hist` stage-D samples of every VFO in front of its next block. The rows are double-buffered by block
+// parity: the history goes from this block's row (cur) to the front of the other parity's row (nxt).
+__global__ void __launch_bounds__(256) xd_shift_kernel(const TailVfo* __restrict__ cur, const TailVfo* __restrict__ nxt) {
+  const TailVfo v = cur[blockIdx.x];
   const int hist = v.hist;
-  float2* row = const_cast<float2*>(v.xd) - hist;
-  for (int base = 0; base < hist; base += 1024) {
-    float2 r[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = base + j * 256 + threadIdx.x;
-      if (i < hist) r[j] = row[v.n_stage + i];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = base + j * 256 + threadIdx.x;
-      if (i < hist) row[i] = r[j];
-    }
-    __syncthreads();
-  }
+  const float2* src = v.xd + v.n_stage - hist;
+  float2* dst = const_cast<float2*>(nxt[blockIdx.x].xd) - hist;
+  for (int i = threadIdx.x; i < hist; i += 256) dst[i] = src[i];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -137,8 +137,9 @@ struct aeroddc_bank {
   float2* d_state[3] = {nullptr, nullptr, nullptr};   // boundary history, rotating by block (the deep kernel of block k still reads
                                                       // state[k % 3] while the main kernel of block k+1 writes state[(k+2) % 3])
   unsigned char* d_vfo_D = nullptr;                   // [vfo_pitch] half-band stages per column
-  float2* d_xd = nullptr;       // all stage-D rows, per VFO: [hist][n_stage]
-  float2** d_xd_rows = nullptr; // [vfo_pitch] pointer to stage-D index 0 of each column's row
+  float2* d_xd = nullptr;       // all stage-D rows, per VFO: [hist][n_stage]; two copies, by block parity, so that block k+1's kernels
+                                // write their rows while block k's tail still reads its own (the history shift copies across)
+  float2** d_xd_rows[2] = {nullptr, nullptr};   // [vfo_pitch] pointer to stage-D index 0 of each column's row, per parity
   float2* d_pw = nullptr;       // tensor mode: [kTcPwRows][vfo_pitch] unit rotation powers u^r
   int* d_nco_len = nullptr;     // [vfo_pitch]
   int* d_post_ctr = nullptr;    // work-item counters of the persistent post-processing kernels: [0] tail, [1 + g] deep kernel of group g
@@ -148,7 +149,7 @@ struct aeroddc_bank {
   int nck_max = 0;
   float* d_taps = nullptr;
   int* d_hil_idx = nullptr;
-  TailVfo* d_tail = nullptr;
+  TailVfo* d_tail[2] = {nullptr, nullptr};   // per block parity (they differ in the stage-D row pointers)
   unsigned char* d_out = nullptr;
   size_t out_total = 0;
   unsigned char* d_in[2] = {nullptr, nullptr};
@@ -221,7 +222,7 @@ void free_all(aeroddc_bank* b) {
   cudaFree(b->d_pw);
   if (b->h_err) cudaFreeHost((void*)b->h_err);
   cudaFree(b->d_dcc_out[0]); cudaFree(b->d_dcc_out[1]); cudaFree(b->d_dcc_state);
-  cudaFree(b->d_xd); cudaFree(b->d_xd_rows); cudaFree(b->d_nco_len); cudaFree(b->d_taps); cudaFree(b->d_hil_idx); cudaFree(b->d_tail); cudaFree(b->d_out);
+  cudaFree(b->d_xd); cudaFree(b->d_xd_rows[0]); cudaFree(b->d_xd_rows[1]); cudaFree(b->d_nco_len); cudaFree(b->d_taps); cudaFree(b->d_hil_idx); cudaFree(b->d_tail[0]); cudaFree(b->d_tail[1]); cudaFree(b->d_out);
   cudaFree(b->d_in[0]); cudaFree(b->d_in[1]);
   for (int i = 0; i < 2; ++i) {
     if (b->h_in[i]) cudaFreeHost(b->h_in[i]);
@@ -281,7 +282,7 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
     d.mid = g.d_mid[par];
     d.state_in = state_in;
     d.state_out = state_out;
-    d.xd_rows = b->d_xd_rows;
+    d.xd_rows = b->d_xd_rows[par];
     d.vfo_D = b->d_vfo_D;
     d.counter = b->d_post_ctr + 1 + (&g - &b->groups[0]);
     d.vfo_pitch = b->vfo_pitch;
@@ -309,7 +310,7 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
     if (g.parent < 0) {
       p.raw = raw;
     } else {   // a sub-VFO group reads its parent's stage-D stream of this block (already enqueued on this stream)
-      p.raw.slice[0] = b->d_xd + b->vfos[g.parent].xd_off + b->vfos[g.parent].hist;
+      p.raw.slice[0] = b->d_xd + (size_t)par * b->xd_total + b->vfos[g.parent].xd_off + b->vfos[g.parent].hist;
       p.raw.n_slices = 1;
       p.raw.slice_len = g.blk_in;
     }
@@ -320,7 +321,7 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
     p.state_out = state_out;
     p.mid = g.direct ? nullptr : g.d_mid[par];
     p.n_mid = g.n_mid;
-    p.xd_rows = b->d_xd_rows;
+    p.xd_rows = b->d_xd_rows[par];
     p.block_abs = k * (long long)g.blk_in;
     p.vfo_pitch = b->vfo_pitch;
     p.vfo_base = g.base;
@@ -378,7 +379,7 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
       t.zone = g.d_mid[par];
       t.state_in = state_in;
       t.state_out = state_out;
-      t.xd_rows = b->d_xd_rows;
+      t.xd_rows = b->d_xd_rows[par];
       t.vfo_D = b->d_vfo_D;
       t.segs = g.d_segs;
       t.cta_seg = g.d_cta_seg;
@@ -392,8 +393,8 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
       t.z0_end = head / 32;
       t.z1_lo = fix_at >= 0 ? fix_at / 32 : 0;
       t.z1_hi = fix_at >= 0 ? std::min((fix_at + zone) / 32, g.n_mid) : 0;
-      // the stage-D rows are single-buffered: the previous block's tail and history shift must be through with them
-      if (k >= 1) CU(cudaStreamWaitEvent(sA, b->ev_post[(k - 1) & 1], 0));
+      // the stage-D rows of this parity were last read by the tail of block k-2
+      if (k >= 2) CU(cudaStreamWaitEvent(sA, b->ev_post[par], 0));
       ddc_tc_kernel<<<(unsigned)g.tc_grid, kTcThreads, kTcSmem, sA>>>(t);
       CU(cudaGetLastError());
       ++launches;
@@ -417,7 +418,7 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
     if (k >= 2) CU(cudaStreamWaitEvent(sB, b->ev_d2h[par], 0));
     const int items = b->tail_chunks * (int)b->vfos.size();
     tail_kernel<<<(unsigned)std::min(items, b->post_ctas_tail), kTailThreads, b->tail_smem, sB>>>(
-        b->d_tail, 1.0f, (size_t)par * b->out_total, b->d_post_ctr, (int)b->vfos.size(), b->tail_chunks);
+        b->d_tail[par], 1.0f, (size_t)par * b->out_total, b->d_post_ctr, (int)b->vfos.size(), b->tail_chunks);
     CU(cudaGetLastError());
     ++launches;
   }
@@ -425,7 +426,7 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
   CU(cudaEventRecord(b->ev_tail[par], sB));
   // keep the last `hist` stage-D samples of every VFO in front of the next block
   if (b->any_hist) {
-    xd_shift_kernel<<<(unsigned)b->vfos.size(), 256, 0, sB>>>(b->d_tail);
+    xd_shift_kernel<<<(unsigned)b->vfos.size(), 256, 0, sB>>>(b->d_tail[par], b->d_tail[par ^ 1]);
     CU(cudaGetLastError());
     ++launches;
   }
@@ -708,12 +709,14 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
   }
   b->out_total = std::max<size_t>(out_off, 16);
   b->xd_total = xd_total;
-  CU(dmalloc((void**)&b->d_xd, sizeof(float2) * xd_total));
-  CU(cudaMemset(b->d_xd, 0, sizeof(float2) * xd_total));
-  std::vector<float2*> h_rows(b->vfo_pitch, b->d_xd);
-  for (const VfoRec& r : b->vfos) h_rows[r.slot] = b->d_xd + r.xd_off + r.hist;
-  CU(dmalloc((void**)&b->d_xd_rows, sizeof(float2*) * b->vfo_pitch));
-  CU(cudaMemcpy(b->d_xd_rows, h_rows.data(), sizeof(float2*) * b->vfo_pitch, cudaMemcpyHostToDevice));
+  CU(dmalloc((void**)&b->d_xd, sizeof(float2) * 2 * xd_total));
+  CU(cudaMemset(b->d_xd, 0, sizeof(float2) * 2 * xd_total));
+  for (int par = 0; par < 2; ++par) {
+    std::vector<float2*> h_rows(b->vfo_pitch, b->d_xd);
+    for (const VfoRec& r : b->vfos) h_rows[r.slot] = b->d_xd + (size_t)par * xd_total + r.xd_off + r.hist;
+    CU(dmalloc((void**)&b->d_xd_rows[par], sizeof(float2*) * b->vfo_pitch));
+    CU(cudaMemcpy(b->d_xd_rows[par], h_rows.data(), sizeof(float2*) * b->vfo_pitch, cudaMemcpyHostToDevice));
+  }
   std::vector<float> h_taps(std::max<size_t>(taps_total, 1));
   std::vector<int> h_idx(std::max<size_t>(idx_total, 1));
   for (const VfoRec& r : b->vfos) {
@@ -762,8 +765,11 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
   b->tail_smem = tail_smem;
   b->tail_chunks = std::max(1, (max_out + kTailChunk - 1) / kTailChunk);
   CU(raise_tail_smem_limit(b->device, tail_smem));
-  CU(dmalloc((void**)&b->d_tail, sizeof(TailVfo) * nv));
-  CU(cudaMemcpy(b->d_tail, h_tail.data(), sizeof(TailVfo) * nv, cudaMemcpyHostToDevice));
+  for (int par = 0; par < 2; ++par) {
+    for (int i = 0; i < nv; ++i) h_tail[i].xd = b->d_xd + (size_t)par * xd_total + b->vfos[i].xd_off + b->vfos[i].hist;
+    CU(dmalloc((void**)&b->d_tail[par], sizeof(TailVfo) * nv));
+    CU(cudaMemcpy(b->d_tail[par], h_tail.data(), sizeof(TailVfo) * nv, cudaMemcpyHostToDevice));
+  }
 
   if (b->dcc) {
     b->dcc_smem = (size_t)prop.sharedMemPerBlockOptin - 1024;   // (almost) everything an SM can give one CTA: no main-kernel CTA fits beside it
@@ -986,7 +992,7 @@ int aeroddc_bank_reset(aeroddc_bank* b) {
   CU(cudaSetDevice(b->device));
   CU(cudaDeviceSynchronize());
   for (int i = 0; i < 3; ++i) CU(cudaMemset(b->d_state[i], 0, sizeof(float2) * (size_t)kMaxStages * kStateSlots * b->vfo_pitch));
-  CU(cudaMemset(b->d_xd, 0, sizeof(float2) * b->xd_total));
+  CU(cudaMemset(b->d_xd, 0, sizeof(float2) * 2 * b->xd_total));
   if (b->d_dcc_state) CU(cudaMemset(b->d_dcc_state, 0, sizeof(float) * 2));
   b->blocks_submitted = b->blocks_done = 0;
   b->cur_out = -1;
@@ -1026,10 +1032,9 @@ int aeroddc_bank_stage_d(aeroddc_bank* b, int vfo, float* host_out, size_t cap_c
   CU(cudaSetDevice(b->device));
   const VfoRec& r = b->vfos[vfo];
   const size_t n = std::min<size_t>(cap_complex, (size_t)r.plan.n_stage);
-  // the block stays at [hist, hist + n_stage) of the row until the next block overwrites it; the
-  // history shift only rewrites [0, hist)
+  // the block stays at [hist, hist + n_stage) of its parity's row until the block after next overwrites it
   CU(cudaStreamSynchronize(b->s_post));
-  CU(cudaMemcpy(host_out, b->d_xd + r.xd_off + r.hist, n * sizeof(float2), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(host_out, b->d_xd + (size_t)((b->blocks_done - 1) & 1) * b->xd_total + r.xd_off + r.hist, n * sizeof(float2), cudaMemcpyDeviceToHost));
   return (int)r.plan.n_stage;
 }
 

@@ -536,9 +536,12 @@ def main():
         e.record()
         events[i] = e
 
+    bank_hosts = {id(bank): host}      # every bank submits from ITS pinned ring (no staging copy on the way)
+
     def run_blocks(bank, n, from_host, on_wait=None):
         """n blocks, two in flight. from_host: the host-facing path (pinned host blocks, H2D of every block inside)."""
         inflight = 0
+        hs = bank_hosts.get(id(bank), host)
         if world > 1 and not peer:
             for k in range(min(2, n)):
                 prefetch_nccl(k, from_host)
@@ -549,7 +552,7 @@ def main():
                     on_wait()
             if world == 1:
                 if from_host:
-                    bank.submit(host[k & 1])
+                    bank.submit(hs[k & 1])
                 else:
                     bank.submit_device(dbuf[k & 1].data_ptr(), None)
             elif peer:
@@ -663,6 +666,11 @@ def main():
     tens = None
     if not args.no_tensor:
         tbank = make_bank(mode=aeroddc.MODE_TENSOR)
+        if world == 1:
+            th = [tbank.host_slot(0), tbank.host_slot(1)]
+            th[0][:] = host[0]
+            th[1][:] = host[1]
+            bank_hosts[id(tbank)] = th
         t_main = []
         run_blocks(tbank, args.warmup, False)
         sync_all()
