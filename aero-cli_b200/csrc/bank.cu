@@ -140,6 +140,7 @@ struct aeroddc_bank {
   float2* d_xd = nullptr;       // all stage-D rows, per VFO: [hist][n_stage]; two copies, by block parity, so that block k+1's kernels
                                 // write their rows while block k's tail still reads its own (the history shift copies across)
   float2** d_xd_rows[2] = {nullptr, nullptr};   // [vfo_pitch] pointer to stage-D index 0 of each column's row, per parity
+  int tc_fstages = 10;
   float2* d_pw = nullptr;       // tensor mode: [kTcPwRows][vfo_pitch] unit rotation powers u^r
   int* d_nco_len = nullptr;     // [vfo_pitch]
   int* d_post_ctr = nullptr;    // work-item counters of the persistent post-processing kernels: [0] tail, [1 + g] deep kernel of group g
@@ -395,7 +396,8 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
       t.z1_hi = fix_at >= 0 ? std::min((fix_at + zone) / 32, g.n_mid) : 0;
       // the stage-D rows of this parity were last read by the tail of block k-2
       if (k >= 2) CU(cudaStreamWaitEvent(sA, b->ev_post[par], 0));
-      ddc_tc_kernel<<<(unsigned)g.tc_grid, kTcThreads, kTcSmem, sA>>>(t);
+      if (b->tc_fstages == 6) ddc_tc_kernel<6><<<(unsigned)g.tc_grid, kTcThreads, TcSmem<6>::kTotal, sA>>>(t);
+      else ddc_tc_kernel<10><<<(unsigned)g.tc_grid, kTcThreads, TcSmem<10>::kTotal, sA>>>(t);
       CU(cudaGetLastError());
       ++launches;
     } else {
@@ -889,7 +891,10 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
       CU(dmalloc((void**)&b->d_pw, sizeof(float2) * (size_t)kTcPwRows * b->vfo_pitch));
       tc_build_pw_kernel<<<dim3((b->vfo_pitch + 127) / 128, kTcPwRows), 128, 0, b->s_compute>>>(b->d_rot, b->vfo_pitch, b->d_pw);
       CU(cudaGetLastError());
-      CU(cudaFuncSetAttribute(ddc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
+      const char* env_fs = getenv("AERODDC_TC_FSTAGES");   // experiments: depth of the filter-slab ring (6 or 10)
+      b->tc_fstages = env_fs && atoi(env_fs) == 6 ? 6 : 10;
+      CU(cudaFuncSetAttribute(ddc_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<6>::kTotal));
+      CU(cudaFuncSetAttribute(ddc_tc_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<10>::kTotal));
       CU(cudaStreamSynchronize(b->s_compute));
     }
     if (d_g) cudaFree(d_g);

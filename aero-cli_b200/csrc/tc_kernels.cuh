@@ -56,9 +56,10 @@ constexpr int kTcXStage = 2 * kTcXPart;               // hi | mid
 constexpr int kTcXStages = 2;
 constexpr int kTcFPart = 2 * kTcRails * 16;           // one bf16 part of a filter slab: [2 chunks][128 rails][16 B]
 constexpr int kTcFSlab = 2 * kTcFPart;                // hi | mid
-constexpr int kTcFStages = 6;
-constexpr int kTcBars = 2 * kTcXStages + 2 * kTcFStages + 4;
-constexpr int kTcSmem = kTcXStages * kTcXStage + kTcFStages * kTcFSlab + 8 * kTcBars + 16;
+template <int FS> struct TcSmem {   // FS = depth of the filter-slab ring
+  static constexpr int kBars = 2 * kTcXStages + 2 * FS + 4;
+  static constexpr int kTotal = kTcXStages * kTcXStage + FS * kTcFSlab + 8 * kBars + 16;
+};
 constexpr int kTcThreads = 320;
 constexpr int kTcPwRows = 512;            // rotation table rows: u^r, r = 0 .. 511
 constexpr int kTcHead = 64;               // outputs [0, kTcHead) of a block (2048 samples) stay on the FP32 kernel
@@ -173,7 +174,9 @@ struct TcWalk {
   }
 };
 
+template <int kTcFStages>
 __global__ void __launch_bounds__(kTcThreads, 1) ddc_tc_kernel(const TcParams p) {
+  constexpr int kTcBars = TcSmem<kTcFStages>::kBars;
   extern __shared__ __align__(1024) unsigned char tsm[];
   unsigned char* xs = tsm;
   unsigned char* fsl = tsm + kTcXStages * kTcXStage;
@@ -211,6 +214,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) ddc_tc_kernel(const TcParams p)
     bool active = false;
     float2* xd = nullptr;
     RailHb hb[kDeepStages];
+    // q for output mc + i: the oscillator state after idx1 + 32 i steps, idx1 = table index of the window's first sample
+    // plus one: exact checkpoint (every 256 steps) times the unit rotation over the remainder. The remainder cycles
+    // through 8 values per 32 outputs (the same 8 all along a stretch: a chunk advances the index by 1024) and the
+    // checkpoint row advances every 8 outputs; the five rows of the NEXT chunk are fetched while this one is processed.
+    // (Indices past the table end only occur in the zones, whose outputs are replaced: clamped, never wrapped.)
+    int idx1 = 1, r0 = -1;
+    float2 pwk[8], ckn[5];
+    const float2* ck_col = p.ckpt;
+    const float2* pw_col = p.pw;
     int tl = 0;
     if (any) do {
       const int a = tl & 1;
@@ -220,6 +232,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) ddc_tc_kernel(const TcParams p)
         col = min(p.vfo_base + slot, p.vfo_pitch - 1);
         nd = max((int)p.vfo_D[col] - kFastStages, 0);
         xd = p.xd_rows[col];
+        ck_col = p.ckpt + col;
+        pw_col = p.pw + col;
+        long long n_s = (p.block_abs + 32ll * w.m0 - kTcLead) % p.nco_len;
+        if (n_s < 0) n_s += p.nco_len;
+        idx1 = (int)n_s + 1;
+        r0 = -1;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) ckn[j] = __ldg(ck_col + (size_t)min((idx1 >> 8) + j, p.nck - 1) * p.vfo_pitch);
 #pragma unroll
         for (int s = 0; s < kDeepStages; ++s) {
 #pragma unroll
@@ -237,9 +257,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) ddc_tc_kernel(const TcParams p)
       }
       mbar_wait(&tfull[a], (tl >> 1) & 1);
       tc_fence_after();
-      const float2* ck_col = p.ckpt + col;
-      const float2* pw_col = p.pw + col;
-      const float2* zone_col = p.zone + (size_t)(slot >> 5) * p.n_mid * 32 + (slot & 31);
+      const int zs = active ? slot : 0;          // lanes beyond the last VFO read VFO 0's zone samples (never stored)
+      const float2* zone_col = p.zone + (size_t)(zs >> 5) * p.n_mid * 32 + (zs & 31);
 #pragma unroll 1
       for (int cb = 0; cb < kTcCols; cb += 32) {
         const int mc = w.m0 + cb;                  // 32 consecutive stage-5 outputs, mc a multiple of 32
@@ -247,20 +266,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) ddc_tc_kernel(const TcParams p)
         float d[32];
         tc_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * kTcCols + cb), d);
         tc_ld_wait();
-        // q for output mc + i: the oscillator state after idx1 + 32 i steps, idx1 = table index of the window's first sample
-        // plus one: exact checkpoint (every 256 steps) times the unit rotation over the remainder. The remainder cycles
-        // through 8 values per 32 outputs and the checkpoint row advances every 8 outputs. (Indices past the table end
-        // only occur in the zones, whose outputs are replaced below: clamped, never wrapped.)
-        long long n_s = (p.block_abs + 32ll * mc - kTcLead) % p.nco_len;
-        if (n_s < 0) n_s += p.nco_len;
-        const int idx1 = (int)n_s + 1;
-        const int c0 = idx1 >> 8, r0 = idx1 & 255;
+        if ((idx1 & 255) != r0) {                   // first chunk of a stretch, or the table restarted inside it
+          r0 = idx1 & 255;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) pwk[k] = __ldg(pw_col + (size_t)((r0 + 32 * k) & 255) * p.vfo_pitch);
+        }
         const int kc = (256 - r0 + 31) >> 5;        // outputs i with (i & 7) >= kc use the next checkpoint row
-        float2 pwk[8], ckc[5];
+        float2 ckc[5];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) pwk[k] = __ldg(pw_col + (size_t)((r0 + 32 * k) & 255) * p.vfo_pitch);
+        for (int j = 0; j < 5; ++j) ckc[j] = ckn[j];
+        idx1 += 1024;
+        if (idx1 > p.nco_len) idx1 -= p.nco_len;
 #pragma unroll
-        for (int j = 0; j < 5; ++j) ckc[j] = __ldg(ck_col + (size_t)min(c0 + j, p.nck - 1) * p.vfo_pitch);
+        for (int j = 0; j < 5; ++j) ckn[j] = __ldg(ck_col + (size_t)min((idx1 >> 8) + j, p.nck - 1) * p.vfo_pitch);
         const bool in_zone = mc < p.z0_end || (mc < p.z1_hi && mc + 32 > p.z1_lo);
         float z[32];
 #pragma unroll
@@ -358,44 +376,51 @@ __global__ void __launch_bounds__(kTcThreads, 1) ddc_tc_kernel(const TcParams p)
   } else if (warp == 8) {
     // ===== filter slabs: one 8 KB bulk copy per k-step =====
     if (lane == 0 && any) {
-      uint32_t it = 0;
+      int fsi = 0;
+      uint32_t fph = 1;                                   // parity to wait for on the empty barrier of slot fsi
       do {
         const unsigned char* src = reinterpret_cast<const unsigned char*>(p.filt) + (size_t)w.nt * kTcKSteps * kTcFSlab;
-        for (int ks = 0; ks < kTcKSteps; ++ks, ++it) {
-          const int fsi = it % kTcFStages;
-          mbar_wait(&fempty[fsi], ((it / kTcFStages) & 1) ^ 1);
+#pragma unroll 4
+        for (int ks = 0; ks < kTcKSteps; ++ks) {
+          mbar_wait(&fempty[fsi], fph);
           mbar_expect_tx(&ffull[fsi], kTcFSlab);
           tma_bulk_g2s(fsl + fsi * kTcFSlab, src + (size_t)ks * kTcFSlab, kTcFSlab, &ffull[fsi]);
+          if (++fsi == kTcFStages) { fsi = 0; fph ^= 1; }
         }
       } while (w.next());
     }
   } else {
     // ===== MMA issuer =====
+    // One thread issues; its loop is the critical path of the kernel (a dependent instruction costs it ~5 cycles, an MMA
+    // runs 128), so everything per k-step is a compile-time constant (the 40 steps are unrolled) or an increment.
     if (lane == 0 && any) {
-      uint32_t it = 0;
+      int fsi = 0;
+      uint32_t fph = 0;                                   // parity to wait for on the full barrier of slot fsi
       int tl = 0;
+      const uint64_t fdesc0 = tc_desc(smem_u32(fsl), kTcRails * 16, 128);
       do {
         const int a = tl & 1, xsi = tl & 1;
         mbar_wait(&tempty[a], ((tl >> 1) & 1) ^ 1);
         mbar_wait(&xfull[xsi], (tl >> 1) & 1);
         tc_fence_after();
         const uint32_t d = tmem + (uint32_t)(a * kTcCols);
-        const uint32_t xhi = smem_u32(xs + xsi * kTcXStage), xmid = xhi + kTcXPart;
-        for (int ks = 0; ks < kTcKSteps; ++ks, ++it) {
-          const int fsi = it % kTcFStages;
-          mbar_wait(&ffull[fsi], (it / kTcFStages) & 1);
+        const uint64_t xdesc_hi = tc_desc(smem_u32(xs + xsi * kTcXStage), kTcRows * 16, 128);
+        const uint64_t xdesc_mid = xdesc_hi + (uint64_t)(kTcXPart >> 4);
+#pragma unroll
+        for (int ks = 0; ks < kTcKSteps; ++ks) {
+          mbar_wait(&ffull[fsi], fph);
           tc_fence_after();
+          constexpr int kDummy = 0; (void)kDummy;
           const int s = 8 + 8 * ks;                       // first sample of the k-step, counted from row (m - 10)
-          const uint32_t xo = (uint32_t)((((s & 31) >> 2) * kTcRows + (s >> 5)) * 16);
-          const uint64_t bh = tc_desc(xhi + xo, kTcRows * 16, 128), bm = tc_desc(xmid + xo, kTcRows * 16, 128);
-          const uint32_t fb = smem_u32(fsl + fsi * kTcFSlab);
-          const uint64_t ah = tc_desc(fb, kTcRails * 16, 128), am = tc_desc(fb + kTcFPart, kTcRails * 16, 128);
-          tc_mma(d, ah, bh, ks > 0);
+          const uint64_t xo = (uint64_t)(((s & 31) >> 2) * kTcRows + (s >> 5));   // in 16-byte units: added to the address field
+          const uint64_t ah = fdesc0 + (uint64_t)(fsi * (kTcFSlab >> 4));
+          tc_mma(d, ah, xdesc_hi + xo, ks > 0);
           if (ks >= kTcCorrLo && ks < kTcCorrHi) {   // the two correction products, where the taps are large enough to matter
-            tc_mma(d, ah, bm, 1);
-            tc_mma(d, am, bh, 1);
+            tc_mma(d, ah, xdesc_mid + xo, 1);
+            tc_mma(d, ah + (uint64_t)(kTcFPart >> 4), xdesc_hi + xo, 1);
           }
           tc_commit(&fempty[fsi]);
+          if (++fsi == kTcFStages) { fsi = 0; fph ^= 1; }
         }
         tc_commit(&xempty[xsi]);
         tc_commit(&tfull[a]);

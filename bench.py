@@ -794,7 +794,7 @@ def main():
             "wall_ms_per_step": wall_ms / args.steps,
         }
         if tens:
-            mma_flops = 3 * 2.0 * (2 * len(mine)) * (BLOCK >> 5) * 640   # three bf16 products x (rails x stage-5 outputs x K = 640) per launch
+            mma_flops = (40 + 2 * 26) / 40.0 * 2.0 * (2 * len(mine)) * (BLOCK >> 5) * 640   # per launch: rails x stage-5 outputs x K = 640, the main bf16 product over 40 k-steps + two correction products over 26
             tol = tens["tol"]
             bf16_peak = None
             if os.path.exists(mp):
@@ -809,7 +809,7 @@ def main():
                              "achieved": mma_flops / (tens["main_ms"] * 1e-3) / 1e12, "peak": bf16_peak,
                              "frac": (mma_flops / (tens["main_ms"] * 1e-3) / 1e12 / bf16_peak) if bf16_peak else None,
                              "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, back to back)",
-                             "note": "achieved = bf16 MMA flops issued (3 products of the hi+mid operand split, K padded 311 -> 320 taps) / time of the "
+                             "note": "achieved = bf16 MMA flops issued (hi x hi over 320 padded taps + two hi x mid correction products over the central 208) / time of the "
                                      "main-stream kernels of a step; the path's algorithmic work is %.1f flop per VFO-sample (FP32 formulation)" % FLOPS_MAIN},
                 "tolerance_vs_exact": None if tol is None else {
                     "vfos": parity["vfos"] if parity else None, "blocks": PARITY_BLOCKS, "int16_max_abs_err_lsb": tol["max_abs_err_lsb"],
