@@ -216,11 +216,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) ddc_tc_kernel(const TcParams p)
     RailHb hb[kDeepStages];
     // q for output mc + i: the oscillator state after idx1 + 32 i steps, idx1 = table index of the window's first sample
     // plus one: exact checkpoint (every 256 steps) times the unit rotation over the remainder. The remainder cycles
-    // through 8 values per 32 outputs (the same 8 all along a stretch: a chunk advances the index by 1024) and the
-    // checkpoint row advances every 8 outputs; the five rows of the NEXT chunk are fetched while this one is processed.
+    // through 8 values per 32 outputs (the same 8 all along a stretch: a chunk advances the index by 1024; taken as
+    // r0 + 32 k without wrapping at 256, so the checkpoint row is simply c0 + i / 8) and the checkpoint row advances
+    // every 8 outputs; the four rows of the NEXT chunk are fetched while this one is processed.
     // (Indices past the table end only occur in the zones, whose outputs are replaced: clamped, never wrapped.)
     int idx1 = 1, r0 = -1;
-    float2 pwk[8], ckn[5];
+    P2 PX[4], PY[4], SPX[4], SPY[4];   // the 8 rotation powers of a chunk, two consecutive outputs per packed register (S* = signed for this rail)
+    float2 ckn[4];
     const float2* ck_col = p.ckpt;
     const float2* pw_col = p.pw;
     int tl = 0;
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ddc_tc_kernel(const TcParams p)
         idx1 = (int)n_s + 1;
         r0 = -1;
 #pragma unroll
-        for (int j = 0; j < 5; ++j) ckn[j] = __ldg(ck_col + (size_t)min((idx1 >> 8) + j, p.nck - 1) * p.vfo_pitch);
+        for (int j = 0; j < 4; ++j) ckn[j] = __ldg(ck_col + (size_t)min((idx1 >> 8) + j, p.nck - 1) * p.vfo_pitch);
 #pragma unroll
         for (int s = 0; s < kDeepStages; ++s) {
 #pragma unroll
@@ -268,28 +270,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) ddc_tc_kernel(const TcParams p)
         tc_ld_wait();
         if ((idx1 & 255) != r0) {                   // first chunk of a stretch, or the table restarted inside it
           r0 = idx1 & 255;
+          const float sg = rail ? 1.f : -1.f;       // rail 0: z = dr fr - di fi; rail 1: z = di fr + dr fi
 #pragma unroll
-          for (int k = 0; k < 8; ++k) pwk[k] = __ldg(pw_col + (size_t)((r0 + 32 * k) & 255) * p.vfo_pitch);
+          for (int kk = 0; kk < 4; ++kk) {
+            const float2 u0 = __ldg(pw_col + (size_t)(r0 + 64 * kk) * p.vfo_pitch), u1 = __ldg(pw_col + (size_t)(r0 + 64 * kk + 32) * p.vfo_pitch);
+            PX[kk] = pack2(u0.x, u1.x); PY[kk] = pack2(u0.y, u1.y);
+            SPX[kk] = pack2(sg * u0.x, sg * u1.x); SPY[kk] = pack2(sg * u0.y, sg * u1.y);
+          }
         }
-        const int kc = (256 - r0 + 31) >> 5;        // outputs i with (i & 7) >= kc use the next checkpoint row
-        float2 ckc[5];
+        float2 ckc[4];
 #pragma unroll
-        for (int j = 0; j < 5; ++j) ckc[j] = ckn[j];
+        for (int j = 0; j < 4; ++j) ckc[j] = ckn[j];
         idx1 += 1024;
         if (idx1 > p.nco_len) idx1 -= p.nco_len;
 #pragma unroll
-        for (int j = 0; j < 5; ++j) ckn[j] = __ldg(ck_col + (size_t)min((idx1 >> 8) + j, p.nck - 1) * p.vfo_pitch);
+        for (int j = 0; j < 4; ++j) ckn[j] = __ldg(ck_col + (size_t)min((idx1 >> 8) + j, p.nck - 1) * p.vfo_pitch);
         const bool in_zone = mc < p.z0_end || (mc < p.z1_hi && mc + 32 > p.z1_lo);
         float z[32];
+        // two consecutive outputs per packed instruction: f = ck * u^r (complex), z = own * Re f -+ partner * Im f
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const bool up = (i & 7) >= kc;
-          const float cx = up ? ckc[(i >> 3) + 1].x : ckc[i >> 3].x, cy = up ? ckc[(i >> 3) + 1].y : ckc[i >> 3].y;
-          const float2 pw = pwk[i & 7];
-          const float fr = cx * pw.x - cy * pw.y, fi = cx * pw.y + cy * pw.x;
-          const float own = d[i], oth = __shfl_xor_sync(0xffffffffu, own, 1);
-          // rail 0: dr fr - di fi (own = dr); rail 1: dr fi + di fr (own = di)
-          z[i] = fmaf(own, fr, oth * (rail ? fi : -fi));
+        for (int j = 0; j < 16; ++j) {
+          const float cx = ckc[j >> 2].x, cy = ckc[j >> 2].y;
+          const P2 fr = fma2(bcast2(-cy), PY[j & 3], mul2s(PX[j & 3], cx));
+          const P2 sf = fma2(bcast2(cy), SPX[j & 3], mul2s(SPY[j & 3], cx));
+          const P2 own = pack2(d[2 * j], d[2 * j + 1]);
+          const P2 oth = pack2(__shfl_xor_sync(0xffffffffu, d[2 * j], 1), __shfl_xor_sync(0xffffffffu, d[2 * j + 1], 1));
+          unpack2(fma2(own, fr, mul2(oth, sf)), z[2 * j], z[2 * j + 1]);
         }
         if (in_zone) {
 #pragma unroll
