@@ -726,6 +726,15 @@ def main():
                 dist.all_reduce(mx, op=dist.ReduceOp.MAX)
                 tens["tol"] = {"max_abs_err_lsb": tens_err_r, "err_power": float(pw[0]), "ref_power": float(pw[1]), "n": int(pw[2]),
                                "stage_err_power": float(pw[3]), "stage_ref_power": float(pw[4]), "stage_max_abs_err": float(mx[0])}
+        n_all = torch.tensor([len(mine)], dtype=torch.int64, device=dev)
+        dist.all_reduce(n_all)
+        assert int(n_all.item()) == args.vfos
+        if parity is not None:
+            allp = [None] * world
+            dist.all_gather_object(allp, parity, group=gloo)
+            parity = {"vfos": sum(p["vfos"] for p in allp), "blocks": PARITY_BLOCKS, "byte_identical": all(p["byte_identical"] for p in allp),
+                      "mismatches": sum(p["mismatches"] for p in allp), "nonzero_payloads": sum(p["nonzero_payloads"] for p in allp),
+                      "against": allp[0]["against"], "exchange": allp[0]["exchange"], "per_rank_vfo_ids": [p["vfo_ids"] for p in allp]}
 
     rc = 0
     if rank == 0:
