@@ -54,6 +54,7 @@ ABI_SYMBOLS = [
     "aeroddc_fleet_device_of", "aeroddc_fleet_destroy", "aeroddc_bank_set_dc_correction", "aeroddc_fleet_set_dc_correction",
     "aeroddc_bank_reset", "aeroddc_fleet_reset", "aeroddc_fleet_exchange", "aeroddc_dev_upload_async", "aeroddc_bank_submit_device_sliced",
     "aeroddc_dev_alloc", "aeroddc_dev_free", "aeroddc_dev_upload", "aeroddc_ipc_export", "aeroddc_ipc_import", "aeroddc_ipc_close", "aeroddc_enable_peer", "aeroddc_plan_segments",
+    "aeroddc_plan_tensor_stretches",
 ]
 
 _lib = None
@@ -89,6 +90,7 @@ def lib():
         L.aeroddc_bank_device_bytes.argtypes = [vp, ctypes.POINTER(cz)]
         L.aeroddc_bank_stopwatch.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_float)]
         L.aeroddc_bank_set_mode.argtypes = [vp, ci]
+        L.aeroddc_plan_tensor_stretches.argtypes = [ci, ci, ci, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ci]
         L.aeroddc_bank_set_dc_correction.argtypes = [vp, ci]
         L.aeroddc_fleet_set_dc_correction.argtypes = [vp, ci]
         L.aeroddc_dev_alloc.argtypes = [ci, cz, ctypes.POINTER(vp)]
@@ -199,6 +201,22 @@ def plan_segments(block_len, decim_count, n_vfos, n_sm=148, waves=1.0, parts=0):
     p = SegmentPlan()
     _check(lib().aeroddc_plan_segments(block_len, decim_count, n_vfos, n_sm, waves, parts, ctypes.byref(p)))
     return {n: getattr(p, n) for n, _ in SegmentPlan._fields_}
+
+
+def plan_tensor_stretches(n_tiles, n_mid, n_sm=148):
+    """Host-side plan of the tensor mode: (number of CTAs, [(cta, tile, first output, end output)])."""
+    L = lib()
+    P = _check(L.aeroddc_plan_tensor_stretches(n_tiles, n_mid, n_sm, None, None, 0))
+    first = (ctypes.c_int * (P + 1))()
+    cap = P + n_tiles + 1
+    flat = (ctypes.c_int * (3 * cap))()
+    n = _check(L.aeroddc_plan_tensor_stretches(n_tiles, n_mid, n_sm, first, flat, cap))
+    out = []
+    for c in range(P):
+        for i in range(first[c], first[c + 1]):
+            out.append((c, flat[3 * i], flat[3 * i + 1], flat[3 * i + 2]))
+    assert len(out) == n
+    return P, out
 
 
 def measure_fp32_peak(device=0):

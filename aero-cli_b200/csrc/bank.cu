@@ -534,6 +534,36 @@ int aeroddc_plan_segments(int block_len, int decim_count, int n_vfos, int n_sm, 
   return AERODDC_OK;
 }
 
+int aeroddc_plan_tensor_stretches(int n_tiles, int n_mid, int n_sm, int* cta_first, int* stretches, int cap) {
+  if (n_tiles < 1 || n_mid < 1 || n_sm < 1) return fail(AERODDC_ERR_ARG, "bad planning arguments");
+  const long long U = (long long)n_tiles * n_mid;
+  const int P = (int)std::max<long long>(1, std::min<long long>(n_sm, U / 1024));
+  if (!cta_first && !stretches) return P;
+  auto bound = [&](int c) -> long long {   // first output (tile-major) of CTA c, cut at a multiple of 256 inside its tile
+    if (c >= P) return U;
+    const long long gg = U * c / P;
+    return gg / n_mid * n_mid + (gg % n_mid) / kTcCols * kTcCols;
+  };
+  int n = 0;
+  for (int c = 0; c < P; ++c) {
+    if (cta_first) cta_first[c] = n;
+    long long gg = bound(c);
+    const long long g1 = bound(c + 1);
+    while (gg < g1) {
+      const int nt = (int)(gg / n_mid), m_lo = (int)(gg % n_mid);
+      const int m_hi = (int)std::min<long long>(n_mid, m_lo + (g1 - gg));
+      if (stretches) {
+        if (n >= cap) return fail(AERODDC_ERR_ARG, "stretch buffer too small");
+        stretches[3 * n] = nt; stretches[3 * n + 1] = m_lo; stretches[3 * n + 2] = m_hi;
+      }
+      ++n;
+      gg += m_hi - m_lo;
+    }
+  }
+  if (cta_first) cta_first[P] = n;
+  return n;
+}
+
 int aeroddc_bank_set_mode(aeroddc_bank* b, int mode) {
   if (!b) return fail(AERODDC_ERR_ARG, "NULL bank");
   if (b->blocks_submitted > 0) return fail(AERODDC_ERR_STATE, "the arithmetic mode cannot change once blocks were processed");
@@ -857,29 +887,12 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
       tc_build_filters_kernel<<<(n + 127) / 128, 128, 0, b->s_compute>>>(b->d_rot, d_g, g.base, g.count, g.tc_ntiles, g.d_filt);
       CU(cudaGetLastError());
       // one contiguous stretch of the (VFO tile, time) plane per CTA, cut at multiples of 256 outputs and at tile ends
-      const long long U = (long long)g.tc_ntiles * g.n_mid;
-      const int P = (int)std::max<long long>(1, std::min<long long>(b->n_sm, U / 1024));
-      auto bound = [&](int c) -> long long {
-        if (c >= P) return U;
-        const long long gg = U * c / P;
-        return gg / g.n_mid * g.n_mid + (gg % g.n_mid) / kTcCols * kTcCols;
-      };
-      std::vector<TcSeg> segs;
-      std::vector<int> cta_seg(P + 1, 0);
-      for (int c = 0; c < P; ++c) {
-        cta_seg[c] = (int)segs.size();
-        long long gg = bound(c);
-        const long long g1 = bound(c + 1);
-        while (gg < g1) {
-          TcSeg sg;
-          sg.nt = (int)(gg / g.n_mid);
-          sg.m_lo = (int)(gg % g.n_mid);
-          sg.m_hi = (int)std::min<long long>(g.n_mid, sg.m_lo + (g1 - gg));
-          segs.push_back(sg);
-          gg += sg.m_hi - sg.m_lo;
-        }
-      }
-      cta_seg[P] = (int)segs.size();
+      const int P = aeroddc_plan_tensor_stretches(g.tc_ntiles, g.n_mid, b->n_sm, nullptr, nullptr, 0);
+      std::vector<int> cta_seg(P + 1, 0), flat(3 * (size_t)(P + g.tc_ntiles) + 3, 0);
+      const int nseg = aeroddc_plan_tensor_stretches(g.tc_ntiles, g.n_mid, b->n_sm, cta_seg.data(), flat.data(), (int)flat.size() / 3);
+      if (nseg < 0) return nseg;
+      std::vector<TcSeg> segs((size_t)nseg);
+      for (int i = 0; i < nseg; ++i) { segs[i].nt = flat[3 * i]; segs[i].m_lo = flat[3 * i + 1]; segs[i].m_hi = flat[3 * i + 2]; }
       g.tc_grid = P;
       CU(dmalloc((void**)&g.d_segs, sizeof(TcSeg) * segs.size()));
       CU(cudaMemcpy(g.d_segs, segs.data(), sizeof(TcSeg) * segs.size(), cudaMemcpyHostToDevice));

@@ -80,6 +80,13 @@ typedef struct aeroddc_segment_plan {
 } aeroddc_segment_plan;
 int aeroddc_plan_segments(int block_len, int decim_count, int n_vfos, int n_sm, double waves, int parts, aeroddc_segment_plan *out);
 
+/* Host-side planning of the tensor mode (below): the (64-VFO tile, stage-5 output) plane of n_tiles x n_mid outputs is cut
+ * into one contiguous run per persistent CTA. With cta_first == stretches == NULL returns the CTA count P (<= n_sm).
+ * Otherwise fills cta_first[P + 1] (stretches of CTA c: [cta_first[c], cta_first[c + 1])) and stretches[3 * i] =
+ * {tile, first output, end output} (first outputs are 0 or multiples of 256) and returns the number of stretches.
+ * Pure host code; replaces nothing in the reference (its loop is per VFO, vfo.cpp:154-186). */
+int aeroddc_plan_tensor_stretches(int n_tiles, int n_mid, int n_sm, int *cta_first, int *stretches, int cap);
+
 /* Arithmetic mode of the half-band/mix/NCO kernel; call before the first block.
  *   AERODDC_MODE_EXACT (default): every multiply and add of the reference, un-fused, in its order:
  *       payloads are byte-identical to the reference's vfo::process chain.

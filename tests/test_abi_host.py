@@ -123,3 +123,34 @@ def test_segment_plan_invariants():
             assert per_group * p["part_len"] >= blk
     with pytest.raises(aeroddc.AeroDdcError):
         aeroddc.plan_segments(57601, 1, 1)
+
+
+@pytest.mark.parametrize("n_tiles,n_mid,n_sm", [(16, 480000, 148), (2, 480000, 148), (1, 12288, 148), (3, 15360, 148), (1, 1024, 148), (5, 99968, 132), (16, 480000, 7)])
+def test_tensor_mode_stretch_plan_covers_every_output_once(n_tiles, n_mid, n_sm):
+    """aeroddc_plan_tensor_stretches (host side of AERODDC_MODE_TENSOR): every (64-VFO tile, stage-5 output) belongs to exactly one
+    stretch, a CTA's stretches are consecutive in tile-major order, stretches start at 0 or at a multiple of 256 (the fused
+    stages' run-in reaches 96 outputs back, never before the block), and the CTAs' loads differ by less than two tiles."""
+    import aeroddc
+
+    P, st = aeroddc.plan_tensor_stretches(n_tiles, n_mid, n_sm)
+    assert 1 <= P <= n_sm
+    cover = {t: [] for t in range(n_tiles)}
+    load = [0] * P
+    last = -1
+    for c, t, lo, hi in st:
+        assert 0 <= t < n_tiles and 0 <= lo < hi <= n_mid
+        assert lo == 0 or (lo % 256 == 0 and lo >= 96)
+        assert hi == n_mid or hi % 256 == 0
+        assert t * n_mid + lo > last                      # tile-major, increasing
+        last = t * n_mid + lo
+        cover[t].append((lo, hi))
+        load[c] += hi - lo
+    for t in range(n_tiles):
+        pos = 0
+        for lo, hi in sorted(cover[t]):
+            assert lo == pos
+            pos = hi
+        assert pos == n_mid
+    assert sum(load) == n_tiles * n_mid
+    busy = [x for x in load if x]
+    assert max(busy) - min(busy) <= 512 or len(busy) == 1
