@@ -199,3 +199,73 @@ def test_tensor_mode_must_be_chosen_before_finalize_and_falls_back_where_it_does
             maxerr, _ = parity_metrics(np.frombuffer(bank.output(i)[0], np.int16), np.frombuffer(o.process(x), np.int16))
             assert maxerr <= 1e-4
     bank.close()
+
+
+def test_tensor_mode_beside_a_main_vfo_with_sub_vfos():
+    """One bank holding a main VFO that feeds sub-VFOs (publisher.cpp:118-219; such a bank runs its kernels in order on one
+    stream) AND flat VFOs with seven / eight stages, which take the tensor path: the sub-VFOs (not eligible: they mix the
+    main VFO's output) stay within tolerance on the FP32 kernels, the flat ones on the tensor kernel."""
+    a = _aeroddc()
+    fs, blk = 1536000, 393216
+    bank = a.Bank(fs, blk, FMT_CF32, 0)
+    fm = -200000.0
+    main = bank.add_vfo(fm, 3, 0, 0, 0.01, 0, 1, 1, "MAIN0")
+    subs = [(15000.0, 2, 0, 0.5), (-22000.0, 1, 0, 0.5)]
+    flats = [(300000.0, 8, 0, 0.5), (-450000.0, 7, 0, 0.5), (123000.0, 6, 0, 0.5)]
+    sub_ids = [bank.add_vfo(f, D, L, 0, g, 1, 1, 1, "SUB%02d" % i, parent=main) for i, (f, D, L, g) in enumerate(subs)]
+    flat_ids = [bank.add_vfo(f, D, L, 0, g, 1, 1, 1, "FLT%02d" % i) for i, (f, D, L, g) in enumerate(flats)]
+    bank.set_mode(a.MODE_TENSOR)
+    bank.finalize()
+    o_main = Oracle(fs, blk, 3, 0, fm, 0.01, 0, 0, 1, 1)
+    o_subs = [Oracle(fs >> 3, blk >> 3, D, L, f, g, 0) for (f, D, L, g) in subs]
+    o_flats = [Oracle(fs, blk, D, L, f, g, 0) for (f, D, L, g) in flats]
+    # tones: inside every flat channel, and inside every sub channel (relative to the main VFO's centre)
+    tones = [(f, 0.15) for (f, D, L, g) in flats] + [(fm + f, 0.15) for (f, D, L, g) in subs]
+    for k in range(5):
+        x = _signal(fs, blk, k, tones, 330)
+        bank.process(x)
+        o_main.process(x)
+        mid = o_main.stage(3)
+        for i, o in zip(sub_ids, o_subs):
+            maxerr, snr = parity_metrics(np.frombuffer(bank.output(i)[0], np.int16), np.frombuffer(o.process(mid), np.int16))
+            assert maxerr <= 1e-4 and snr >= 80.0, (i, k, maxerr, snr)
+        for i, o, (f, D, L, g) in zip(flat_ids, o_flats, flats):
+            want = np.frombuffer(o.process(x), np.int16)
+            maxerr, snr = parity_metrics(np.frombuffer(bank.output(i)[0], np.int16), want)
+            assert maxerr <= 1e-4 and snr >= 80.0, (i, k, maxerr, snr)
+            sg = bank.stage_d(i, blk >> D).astype(np.float64)
+            so = o.stage(D).astype(np.float64)
+            assert 10 * np.log10((so * so).sum() / max(((sg - so) ** 2).sum(), 1e-300)) >= 100.0, (i, k)
+    bank.close()
+
+
+def test_fleet_in_tensor_mode_equals_the_single_bank():
+    """The native multi-GPU layer in tensor mode (two GPUs: the raw block lies in one slice per GPU and the tensor kernel's
+    staging loads read both over NVLink): every VFO's payload equals the single-bank tensor run bit for bit (same kernel,
+    same arithmetic, only the block's location differs). Degenerates to one GPU where there is only one."""
+    import torch
+
+    a = _aeroddc()
+    ndev = min(2, torch.cuda.device_count())
+    fs, blk = 2400000, 491520
+    rng = np.random.default_rng(77)
+    freqs = rng.integers(int(-0.45 * fs), int(0.45 * fs), 70).astype(np.float64)
+    vfos = [(float(freqs[i]), [8, 7, 6][i % 3], 0, 0.5) for i in range(70)]
+    fleet = a.Fleet(fs, blk, a.CF32, tuple(range(ndev)))
+    bank = a.Bank(fs, blk, a.CF32, 0)
+    for i, (f, D, L, g) in enumerate(vfos):
+        fleet.add_vfo(f, D, L, 0, g, 1, 1, 1, "Q%04d" % i)
+        bank.add_vfo(f, D, L, 0, g, 1, 1, 1, "Q%04d" % i)
+    fleet.set_mode(a.MODE_TENSOR)
+    bank.set_mode(a.MODE_TENSOR)
+    fleet.finalize()
+    bank.finalize()
+    tones = [(vfos[i][0], 0.05) for i in range(0, 70, 7)]
+    for k in range(3):
+        x = _signal(fs, blk, k, tones, 770)
+        fleet.process(x)
+        bank.process(x)
+        for i in range(70):
+            assert fleet.output(i) == bank.output(i), (i, k)
+    fleet.close()
+    bank.close()
