@@ -349,31 +349,56 @@ __global__ void __launch_bounds__(kTcThreads, 1) ddc_tc_kernel(const TcParams p)
     } while (w.next());
   } else if (warp < 8) {
     // ===== X producer: rows of the raw block -> bf16 hi / mid, [chunk][row][16 B] =====
+    // A tile needs rows m0-10 .. m0+255. The 256 body rows come from global memory, two rows per thread with all 32
+    // 16-byte loads of both in flight at once (the block may live on another GPU: one NVLink round trip per tile, not
+    // three); the 10 halo rows in front are the last 10 body rows of the previous tile of the stretch, which still sit,
+    // converted, in the other stage.
     const int ptid = threadIdx.x - 128;
     int tl = 0;
+    auto fetch_row = [&](int rho, float4 (&r)[16]) {
+      const bool valid = rho >= 0 && rho < p.n_mid;
+      const int g0 = (valid ? rho : 0) * 32;
+      const int sl = p.raw.n_slices > 1 ? g0 / p.raw.slice_len : 0;
+      const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(p.raw.slice[sl]) + (g0 - sl * p.raw.slice_len));
+#pragma unroll
+      for (int c = 0; c < 16; ++c) r[c] = valid ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto store_row = [&](unsigned char* hi_base, int i, const float4 (&r)[16]) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 h, mdl;
+        split_pair(r[2 * c].x, r[2 * c].y, h.x, mdl.x);
+        split_pair(r[2 * c].z, r[2 * c].w, h.y, mdl.y);
+        split_pair(r[2 * c + 1].x, r[2 * c + 1].y, h.z, mdl.z);
+        split_pair(r[2 * c + 1].z, r[2 * c + 1].w, h.w, mdl.w);
+        *reinterpret_cast<uint4*>(hi_base + (c * kTcRows + i) * 16) = h;
+        *reinterpret_cast<uint4*>(hi_base + kTcXPart + (c * kTcRows + i) * 16) = mdl;
+      }
+    };
     if (any) do {
       const int xsi = tl & 1;
       const int row0 = w.m0 - kTcBack;
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // every producer thread is through with the previous tile (its rows are read below)
       mbar_wait(&xempty[xsi], ((tl >> 1) & 1) ^ 1);
       unsigned char* hi_base = xs + xsi * kTcXStage;
-      for (int i = ptid; i < kTcCols + kTcBack; i += 128) {
-        const int rho = row0 + i;
-        const bool valid = rho >= 0 && rho < p.n_mid;
-        const int g0 = (valid ? rho : 0) * 32;
-        const int sl = p.raw.n_slices > 1 ? g0 / p.raw.slice_len : 0;
-        const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(p.raw.slice[sl]) + (g0 - sl * p.raw.slice_len));
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
-          if (valid) { u = __ldg(src + 2 * c); v = __ldg(src + 2 * c + 1); }
-          uint4 h, mdl;
-          split_pair(u.x, u.y, h.x, mdl.x);
-          split_pair(u.z, u.w, h.y, mdl.y);
-          split_pair(v.x, v.y, h.z, mdl.z);
-          split_pair(v.z, v.w, h.w, mdl.w);
-          *reinterpret_cast<uint4*>(hi_base + (c * kTcRows + i) * 16) = h;
-          *reinterpret_cast<uint4*>(hi_base + kTcXPart + (c * kTcRows + i) * 16) = mdl;
+      {
+        float4 ra[16], rb[16];
+        fetch_row(row0 + kTcBack + ptid, ra);
+        fetch_row(row0 + kTcBack + 128 + ptid, rb);
+        store_row(hi_base, kTcBack + ptid, ra);
+        store_row(hi_base, kTcBack + 128 + ptid, rb);
+      }
+      if (w.seg_first) {
+        if (ptid < kTcBack) {
+          float4 r[16];
+          fetch_row(row0 + ptid, r);
+          store_row(hi_base, ptid, r);
         }
+      } else if (ptid < 8 * kTcBack) {
+        const unsigned char* prev = xs + (xsi ^ 1) * kTcXStage;
+        const int row = ptid >> 3, c = ptid & 7;
+        *reinterpret_cast<uint4*>(hi_base + (c * kTcRows + row) * 16) = *reinterpret_cast<const uint4*>(prev + (c * kTcRows + kTcCols + row) * 16);
+        *reinterpret_cast<uint4*>(hi_base + kTcXPart + (c * kTcRows + row) * 16) = *reinterpret_cast<const uint4*>(prev + kTcXPart + (c * kTcRows + kTcCols + row) * 16);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's reads
       mbar_arrive(&xfull[xsi]);

@@ -12,7 +12,7 @@
  *   tail            = late FIR / delay - Hilbert / fir_usb / int16 (vfo.cpp:188-258, dsp.cpp:64-78,216-231)
  *
  * Pinned against: the SURVEY.md section-8c golden anchors and oracle/_ref/libref_vfo.so (the
- * unmodified reference compiled here) by tests/test_oracle_vs_reference.py and the fixtures in
+ * unmodified reference compiled here) by tests/test_oracle_golden.py and the fixtures in
  * tests/golden/. Build: gcc -std=c11 -O2 -ffp-contract=off (never -ffast-math; FMA contraction
  * changes the output bits, SURVEY.md finding 4).
  *
