@@ -141,6 +141,7 @@ struct aeroddc_bank {
                                 // write their rows while block k's tail still reads its own (the history shift copies across)
   float2** d_xd_rows[2] = {nullptr, nullptr};   // [vfo_pitch] pointer to stage-D index 0 of each column's row, per parity
   int tc_fstages = 10;
+  bool gather = false;           // sliced blocks are first gathered into local HBM by the copy engines (tensor mode, see submit_device_sliced)
   float2* d_pw = nullptr;       // tensor mode: [kTcPwRows][vfo_pitch] unit rotation powers u^r
   int* d_nco_len = nullptr;     // [vfo_pitch]
   int* d_post_ctr = nullptr;    // work-item counters of the persistent post-processing kernels: [0] tail, [1 + g] deep kernel of group g
@@ -912,6 +913,12 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
     }
     if (d_g) cudaFree(d_g);
   }
+  {
+    bool any_tc = false;
+    for (const Group& g : b->groups) any_tc = any_tc || g.tc_ntiles > 0;
+    const char* env_g = getenv("AERODDC_GATHER");   // experiments: 0 = always read slices in place, 1 = always gather
+    b->gather = env_g ? atoi(env_g) != 0 : any_tc;
+  }
   b->dev_bytes = bytes;
   b->finalized = true;
   return AERODDC_OK;
@@ -939,6 +946,29 @@ int aeroddc_bank_submit_device_sliced(aeroddc_bank* b, const void* const* slices
   raw.slice_len = n_slices > 1 ? (int)slice_len : b->B;
   CU(cudaSetDevice(b->device));
   cudaStream_t first = b->dcc ? b->s_dcc : b->s_compute;
+  if (n_slices > 1 && b->gather) {
+    // Tensor mode reads every raw sample once per 64-VFO tile and finishes a block in a fraction of a millisecond per
+    // GPU: pulled in place, the tiles of one GPU would cross NVLink (V / N / 64) times and the links, not the tensor
+    // pipe, would set the pace (measured: 0.89 ms per block at 8 GPUs against 0.45 ms for the same shard fed from local
+    // HBM). So the copy engines gather the slices into the bank's own input buffer first - each byte crosses NVLink once,
+    // on the copy stream, while the previous block computes - and the kernels read local memory.
+    const int par = (int)(b->blocks_submitted & 1);   // d_in[par] was last read by the block submitted two calls ago (retired)
+    const size_t bps = b->in_bytes / (size_t)b->B;
+    for (int i = 0; i < n_events; ++i)
+      if (ready_events[i]) CU(cudaStreamWaitEvent(b->s_copy, (cudaEvent_t)ready_events[i], 0));
+    for (int i = 0; i < n_slices; ++i) {
+      const size_t off = (size_t)i * slice_len;
+      const size_t cnt = std::min(slice_len, (size_t)b->B - off);
+      CU(cudaMemcpyAsync(b->d_in[par] + off * bps, slices[i], cnt * bps, cudaMemcpyDefault, b->s_copy));
+    }
+    CU(cudaEventRecord(b->ev_h2d[par], b->s_copy));
+    CU(cudaStreamWaitEvent(first, b->ev_h2d[par], 0));
+    for (int i = 0; i < kMaxSlices; ++i) raw.slice[i] = nullptr;
+    raw.slice[0] = b->d_in[par];
+    raw.n_slices = 1;
+    raw.slice_len = b->B;
+    return enqueue_block(b, raw);
+  }
   for (int i = 0; i < n_events; ++i)
     if (ready_events[i]) CU(cudaStreamWaitEvent(first, (cudaEvent_t)ready_events[i], 0));
   return enqueue_block(b, raw);

@@ -407,6 +407,12 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # stdout carries the one JSON line and nothing else: libraries that write to file descriptor 1 (NCCL prints its version
+    # banner there) are sent to stderr, the line itself goes to a private copy of the original descriptor
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -814,6 +820,8 @@ def main():
                         "d2h_bytes_per_step": int(args.vfos * (BLOCK >> DECIM) // LATE * 2)},
                 "realtime_x": total / (tens["ms"] * 1e-3) / (args.vfos * FS),
                 "main_ms": tens["main_ms"], "launches_per_step": tens["launches"],
+                "exchange": ("peer slices gathered into the bank's local input buffer by the copy engines over NVLink (each byte crosses once, "
+                             "one block ahead on the copy stream), kernels read local HBM" if peer else ("nccl" if world > 1 else "local")),
                 "roofline": {"bound": "tensor", "kernel": "ddc_tc_kernel (+ the FP32 launch over the block head)", "unit": "TFLOP/s",
                              "achieved": mma_flops / (tens["main_ms"] * 1e-3) / 1e12, "peak": bf16_peak,
                              "frac": (mma_flops / (tens["main_ms"] * 1e-3) / 1e12 / bf16_peak) if bf16_peak else None,
@@ -841,7 +849,8 @@ def main():
             cb = line.get("cpu_baseline")
             line["configs"] = side_configs(aeroddc, torch, dev, local_rank, peak_tflops,
                                            None if cb is None else {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")})
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
         if parity is not None and not parity["byte_identical"]:
             sys.stderr.write("bench.py: PARITY FAILURE: %d payloads differ from the reference chain\n" % parity["mismatches"])
             rc = 1

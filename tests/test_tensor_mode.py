@@ -82,11 +82,17 @@ def test_tensor_mode_wideband_mixed_stage_counts_across_the_table_restart():
     bank.close()
 
 
-def test_tensor_mode_table_restart_inside_a_block_and_sliced_input():
+@pytest.mark.parametrize("gather", ["default", "0"])
+def test_tensor_mode_table_restart_inside_a_block_and_sliced_input(gather, monkeypatch):
     """1.536 MS/s with blocks of 393216 samples: the oscillator table (1 536 000 entries) restarts in the middle of block 3,
     beyond the block head - the FP32 kernel takes over a second zone there. The raw block is handed over in three device
-    slices (on a node: one per GPU, read over NVLink), as bench.py's peer exchange does."""
+    slices (on a node: one per GPU), as bench.py's peer exchange does: by default the bank's copy engines gather them into
+    its local input buffer first; with AERODDC_GATHER=0 the kernels' own loads read every slice in place."""
     a = _aeroddc()
+    if gather == "0":
+        monkeypatch.setenv("AERODDC_GATHER", "0")
+    else:
+        monkeypatch.delenv("AERODDC_GATHER", raising=False)
     fs, blk = 1536000, 393216
     rng = np.random.default_rng(15)
     freqs = rng.integers(int(-0.45 * fs), int(0.45 * fs), 40).astype(np.float64)
@@ -240,8 +246,8 @@ def test_tensor_mode_beside_a_main_vfo_with_sub_vfos():
 
 
 def test_fleet_in_tensor_mode_equals_the_single_bank():
-    """The native multi-GPU layer in tensor mode (two GPUs: the raw block lies in one slice per GPU and the tensor kernel's
-    staging loads read both over NVLink): every VFO's payload equals the single-bank tensor run bit for bit (same kernel,
+    """The native multi-GPU layer in tensor mode (two GPUs: the raw block lies in one slice per GPU and every bank's copy
+    engines gather both over NVLink into its local input buffer before its kernels start): every VFO's payload equals the single-bank tensor run bit for bit (same kernel,
     same arithmetic, only the block's location differs). Degenerates to one GPU where there is only one."""
     import torch
 
