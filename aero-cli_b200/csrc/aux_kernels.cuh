@@ -209,73 +209,160 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(const TailVfo* __res
 
 // DC removal of Publisher::demodData (publisher.cpp:292-296), exact and therefore sequential:
 //   avept = avept * (1.0f - 0.000001f) + 0.000001f * x;  x -= avept      (std::complex<float> ops = per rail)
-// Lane 0 walks the I rail and lane 1 the Q rail (one dependent FMUL + FADD per sample); the running average persists in
-// `state` across blocks. All 32 lanes feed them: a batch is 32 consecutive raw values (16 complex samples, one coalesced
-// load), kDccAhead batches are in flight in registers, the two rails pick their values out of a batch with shuffles one
-// batch ahead of the recurrence, and every lane corrects and stores its own value (one coalesced store per batch) with
-// the averages the two rails leave in shared memory. Measured: 165 ms per 15.36 M-sample block (the pointer-chasing
-// one-thread-per-rail form of this loop waited for memory at every sample: 1.17 s).
-// The block may come in slices (RawBlock, ddc_kernels.cuh; slice lengths are multiples of 32 samples).
-constexpr int kDccAhead = 16;
+// The only serial part is one dependent FMUL + FADD per sample and rail (8 cycles); everything else is taken off that
+// chain by a three-warp pipeline over batches of kDccBatch samples in shared memory (mbarrier ring, kDccStages deep):
+//   warp 1  loads the raw batch (coalesced 16-byte loads, from whichever slice of the block holds it), converts it,
+//           keeps x and the products t = 0.000001f * x, the latter de-interleaved per rail;
+//   warp 0  walks the recurrence: lane 0 the I rail, lane 1 the Q rail; four samples per LDS.128 of t (loaded one group
+//           ahead), four FMUL + FADD pairs, one STS.128 of the four running averages - 2.5 instructions per sample
+//           beside the 8-cycle dependency, on a scheduler it has to itself;
+//   warp 2  subtracts the averages from x and stores the corrected cf32 block (coalesced 16-byte stores).
+// The running average persists in `state` across blocks. Before (one warp doing all three jobs, values handed round by
+// shuffles): 163 ms per 15.36 M-sample block, now 80 ms (the dependent pair costs 10.2 cycles per sample at the nominal clock;
+// FFMA forms of the two operations and deeper prefetch of t were measured and change nothing); round 1 (one thread per rail
+// chasing pointers): 1.2 s.
+constexpr int kDccBatch = 1024;    // complex samples per batch
+constexpr int kDccStages = 4;
+constexpr int kDccThreads = 96;
+constexpr int kDccStageBytes = 3 * 2 * kDccBatch * (int)sizeof(float);   // x (interleaved) | t (per rail) | averages (per rail)
+constexpr int kDccSmemMin = kDccStages * kDccStageBytes + 3 * kDccStages * 8;
 
-template <int FMT> __device__ __forceinline__ float dcc_load(const void* raw, size_t i) {
-  if (FMT == 0) return __fdiv_rn(__fsub_rn((float)reinterpret_cast<const unsigned char*>(raw)[i], 127.4f), 128.0f);
-  if (FMT == 1) return __fdiv_rn((float)reinterpret_cast<const short*>(raw)[i], 32768.0f);
-  return reinterpret_cast<const float*>(raw)[i];
+__device__ __forceinline__ void dcc_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// two consecutive complex samples (s, s + 1) of the block as floats; s is even, slices hold an even number of samples
+template <int FMT> __device__ __forceinline__ float4 dcc_load2(const RawBlock& rb, int s, int n) {
+  const void* base = rb.slice[0];
+  int s_in = s;
+#pragma unroll
+  for (int k = 1; k < kMaxSlices; ++k)                  // static indices into the parameter block
+    if (k < rb.n_slices && s >= k * rb.slice_len) { base = rb.slice[k]; s_in = s - k * rb.slice_len; }
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (s + 1 < n) {
+    if (FMT == 2) {
+      v = __ldg(reinterpret_cast<const float4*>(base) + (s_in >> 1));
+    } else if (FMT == 1) {
+      const short4 r = __ldg(reinterpret_cast<const short4*>(base) + (s_in >> 1));
+      v = make_float4(cvt_s16(r.x), cvt_s16(r.y), cvt_s16(r.z), cvt_s16(r.w));
+    } else {
+      const uchar4 r = __ldg(reinterpret_cast<const uchar4*>(base) + (s_in >> 1));
+      v = make_float4(cvt_u8(r.x), cvt_u8(r.y), cvt_u8(r.z), cvt_u8(r.w));
+    }
+  } else if (s < n) {
+    const float2 h = load_raw<FMT>(base, (size_t)s_in);
+    v.x = h.x; v.y = h.y;
+  }
+  return v;
 }
 
 template <int FMT>
-__device__ __forceinline__ float dcc_walk(const void* raw, float* __restrict__ o, int m, int lane, float a, float (*avg)[32]) {
-  const int rail = lane & 1;
-  const float k = 1.0f - 0.000001f, c = 0.000001f;
-  const int nb = m / 16;                               // batches of 32 raw values (m is a multiple of 16)
-  float buf[kDccAhead];
+__global__ void __launch_bounds__(kDccThreads) dcc_kernel(const RawBlock rb, float* __restrict__ out, float* __restrict__ state, int n) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  uint64_t* full_t = reinterpret_cast<uint64_t*>(dsm + kDccStages * kDccStageBytes);
+  uint64_t* full_a = full_t + kDccStages;
+  uint64_t* empty = full_a + kDccStages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3 * kDccStages; ++i) mbar_init(&full_t[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int nbatch = (n + kDccBatch - 1) / kDccBatch;
+  constexpr int kPairs = kDccBatch / 64;                 // float4 (two samples) per lane and batch
+
+  if (warp == 1) {
+    // ---- loads, conversion, t = c * x ----
+    const float cc = 0.000001f;
+    for (int bt = 0; bt < nbatch; ++bt) {
+      const int st = bt % kDccStages;
+      float* xs = reinterpret_cast<float*>(dsm + st * kDccStageBytes);
+      float* ts = xs + 2 * kDccBatch;
+      float4 v[kPairs];
 #pragma unroll
-  for (int j = 0; j < kDccAhead; ++j) buf[j] = j < nb ? dcc_load<FMT>(raw, (size_t)j * 32 + lane) : 0.0f;
-  float xn[16];
+      for (int i = 0; i < kPairs; ++i) v[i] = dcc_load2<FMT>(rb, bt * kDccBatch + 2 * (lane + 32 * i), n);
+      mbar_wait(&empty[st], ((unsigned)(bt / kDccStages) & 1u) ^ 1u);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) xn[i] = __shfl_sync(0xffffffffu, buf[0], 2 * i + rail);
-  for (int b0 = 0; b0 < nb; b0 += kDccAhead) {
-#pragma unroll
-    for (int j = 0; j < kDccAhead; ++j) {
-      const int bt = b0 + j;
-      float xc[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) xc[i] = xn[i];
-      const float mine = buf[j];                         // this lane's own raw value of batch bt
-      if (bt + kDccAhead < nb) buf[j] = dcc_load<FMT>(raw, (size_t)(bt + kDccAhead) * 32 + lane);   // uniform
-#pragma unroll
-      for (int i = 0; i < 16; ++i) xn[i] = __shfl_sync(0xffffffffu, buf[(j + 1) % kDccAhead], 2 * i + rail);
-      if (bt < nb) {                                     // uniform
-        float* av = avg[j & 1];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          a = __fadd_rn(__fmul_rn(a, k), __fmul_rn(c, xc[i]));
-          if (lane < 2) av[2 * i + rail] = a;            // the running average after sample i of the batch, per rail
-        }
-        __syncwarp();
-        o[(size_t)bt * 32 + lane] = __fsub_rn(mine, av[lane]);
+      for (int i = 0; i < kPairs; ++i) {
+        const int q = lane + 32 * i;                      // samples 2q, 2q + 1 of the batch
+        reinterpret_cast<float4*>(xs)[q] = v[i];
+        reinterpret_cast<float2*>(ts)[q] = make_float2(__fmul_rn(cc, v[i].x), __fmul_rn(cc, v[i].z));
+        reinterpret_cast<float2*>(ts + kDccBatch)[q] = make_float2(__fmul_rn(cc, v[i].y), __fmul_rn(cc, v[i].w));
       }
+      __syncwarp();
+      if (lane == 0) dcc_arrive(&full_t[st]);
     }
-  }
-  return a;
-}
-
-template <int FMT>
-__global__ void __launch_bounds__(32) dcc_kernel(const RawBlock rb, float* __restrict__ out, float* __restrict__ state, int n) {
-  __shared__ float avg[2][32];
-  const int lane = threadIdx.x;
-  float a = state[lane & 1];
-  int done = 0;
+  } else if (warp == 0) {
+    // ---- the recurrence ----
+    const int rail = lane & 1;
+    const float kk = 1.0f - 0.000001f;
+    float a = state[rail];
+    for (int bt = 0; bt < nbatch; ++bt) {
+      const int st = bt % kDccStages;
+      const unsigned ph = (unsigned)(bt / kDccStages) & 1u;
+      float* xs = reinterpret_cast<float*>(dsm + st * kDccStageBytes);
+      const float4* tp = reinterpret_cast<const float4*>(xs + 2 * kDccBatch + rail * kDccBatch);
+      float4* ap = reinterpret_cast<float4*>(xs + 4 * kDccBatch + rail * kDccBatch);
+      const int m = min(kDccBatch, n - bt * kDccBatch);
+      const int g8 = m >> 3;
+      mbar_wait(&full_t[st], ph);
+      // eight samples per turn; their products are loaded TWO turns (130 cycles) ahead: the warp issues in order, so a
+      // shared-memory load still in flight when its first use comes up would stall the chain itself
+      float4 b0 = tp[0], b1 = tp[1], c0 = tp[2], c1 = tp[3];
+#pragma unroll 3
+      for (int g = 0; g < g8; ++g) {
+        const float4 t0 = b0, t1 = b1;
+        b0 = c0; b1 = c1;
+        const int nx = min(2 * g + 4, kDccBatch / 4 - 2);
+        c0 = tp[nx]; c1 = tp[nx + 1];
+        float4 r0, r1;
+        a = __fadd_rn(__fmul_rn(a, kk), t0.x); r0.x = a;
+        a = __fadd_rn(__fmul_rn(a, kk), t0.y); r0.y = a;
+        a = __fadd_rn(__fmul_rn(a, kk), t0.z); r0.z = a;
+        a = __fadd_rn(__fmul_rn(a, kk), t0.w); r0.w = a;
+        if (lane < 2) ap[2 * g] = r0;
+        a = __fadd_rn(__fmul_rn(a, kk), t1.x); r1.x = a;
+        a = __fadd_rn(__fmul_rn(a, kk), t1.y); r1.y = a;
+        a = __fadd_rn(__fmul_rn(a, kk), t1.z); r1.z = a;
+        a = __fadd_rn(__fmul_rn(a, kk), t1.w); r1.w = a;
+        if (lane < 2) ap[2 * g + 1] = r1;
+      }
+      if (m & 7) {                                        // ragged end of the block
+        const float* t1 = reinterpret_cast<const float*>(tp);
+        float* a1 = reinterpret_cast<float*>(ap);
+        for (int i = g8 * 8; i < m; ++i) {
+          a = __fadd_rn(__fmul_rn(a, kk), t1[i]);
+          if (lane < 2) a1[i] = a;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) dcc_arrive(&full_a[st]);
+    }
+    if (lane < 2) state[lane] = a;
+  } else {
+    // ---- x - avept, stores ----
+    for (int bt = 0; bt < nbatch; ++bt) {
+      const int st = bt % kDccStages;
+      const unsigned ph = (unsigned)(bt / kDccStages) & 1u;
+      const float* xs = reinterpret_cast<const float*>(dsm + st * kDccStageBytes);
+      const float* as = xs + 4 * kDccBatch;
+      mbar_wait(&full_a[st], ph);
 #pragma unroll
-  for (int s = 0; s < kMaxSlices; ++s) {               // static index into the parameter block
-    if (s < rb.n_slices && done < n) {
-      const int m = min(rb.slice_len, n - done);
-      a = dcc_walk<FMT>(rb.slice[s], out + 2 * (size_t)done, m, lane, a, avg);
-      done += m;
+      for (int i = 0; i < kPairs; ++i) {
+        const int q = lane + 32 * i;
+        const int s = bt * kDccBatch + 2 * q;
+        const float4 x = reinterpret_cast<const float4*>(xs)[q];
+        const float2 ar = reinterpret_cast<const float2*>(as)[q];
+        const float2 ai = reinterpret_cast<const float2*>(as + kDccBatch)[q];
+        if (s + 1 < n)
+          reinterpret_cast<float4*>(out)[(size_t)s >> 1] = make_float4(__fsub_rn(x.x, ar.x), __fsub_rn(x.y, ai.x), __fsub_rn(x.z, ar.y), __fsub_rn(x.w, ai.y));
+        else if (s < n)
+          reinterpret_cast<float2*>(out)[s] = make_float2(__fsub_rn(x.x, ar.x), __fsub_rn(x.y, ai.x));
+      }
+      __syncwarp();
+      if (lane == 0) dcc_arrive(&empty[st]);
     }
   }
-  if (lane < 2) state[lane] = a;
 }
 
 // Keep the last `hist` stage-D samples of every VFO in front of its next block. The rows are double-buffered by block

@@ -257,13 +257,14 @@ int enqueue_block(aeroddc_bank* b, const RawBlock& raw_in) {
   int raw_fmt = b->fmt;
   if (b->dcc) {
     // Sequential DC removal of the raw stream, one block ahead of the VFOs, which then read the corrected cf32 block.
-    // The recurrence is one dependent FMUL + FADD per sample; next to 16 warps that saturate the FP32 pipe its single
-    // warp would be starved (measured: 19x slower), so the CTA asks for a whole SM's shared memory and thereby keeps
-    // the SM to itself: 1/148 of the machine for the rate-limiting step of a DC-corrected stream.
+    // The recurrence is one dependent FMUL + FADD per sample; next to 16 warps that saturate the FP32 pipe its warp
+    // would be starved (measured: 19x slower), so the CTA (recurrence warp + a loading and a storing warp, dcc_kernel)
+    // asks for a whole SM's shared memory and thereby keeps the SM to itself: 1/148 of the machine for the rate-limiting
+    // step of a DC-corrected stream.
     const size_t ex = b->dcc_smem;
-    if (b->fmt == AERODDC_CU8) dcc_kernel<0><<<1, 32, ex, b->s_dcc>>>(raw, b->d_dcc_out[par], b->d_dcc_state, b->B);
-    else if (b->fmt == AERODDC_CS16) dcc_kernel<1><<<1, 32, ex, b->s_dcc>>>(raw, b->d_dcc_out[par], b->d_dcc_state, b->B);
-    else dcc_kernel<2><<<1, 32, ex, b->s_dcc>>>(raw, b->d_dcc_out[par], b->d_dcc_state, b->B);
+    if (b->fmt == AERODDC_CU8) dcc_kernel<0><<<1, kDccThreads, ex, b->s_dcc>>>(raw, b->d_dcc_out[par], b->d_dcc_state, b->B);
+    else if (b->fmt == AERODDC_CS16) dcc_kernel<1><<<1, kDccThreads, ex, b->s_dcc>>>(raw, b->d_dcc_out[par], b->d_dcc_state, b->B);
+    else dcc_kernel<2><<<1, kDccThreads, ex, b->s_dcc>>>(raw, b->d_dcc_out[par], b->d_dcc_state, b->B);
     CU(cudaGetLastError());
     ++launches;
     CU(cudaEventRecord(b->ev_dcc[par], b->s_dcc));

@@ -380,35 +380,55 @@ def test_many_vfos_three_decimations_two_formats():
     bank.close()
 
 
-@pytest.mark.parametrize("fmt", [FMT_CU8, FMT_CF32])
+@pytest.mark.parametrize("fmt", [FMT_CU8, FMT_CS16, FMT_CF32])
 def test_dc_correction_vs_oracle(fmt):
     """--enable-dcc / correct_dc_bias=1: the sequential first-order DC removal of Publisher::demodData
-    (publisher.cpp:292-296) on the GPU, state carried across blocks, then the normal chain."""
+    (publisher.cpp:292-296) on the GPU, state carried across blocks, then the normal chain. The block length is not a
+    multiple of the DC kernel's 1024-sample batches (ragged last batch). A second bank gets the same blocks in three
+    device slices whose borders fall inside a batch."""
     from oracle_bind import dc_correct
 
     a = _aeroddc()
     fs, blk = 288000, 57600
     vfos = [dict(mixer=1234.0, D=2, L=0, gain=0.5), dict(mixer=-40000.0, D=1, L=6, gain=0.4)]
-    bank = a.Bank(fs, blk, fmt, 0)
-    for i, v in enumerate(vfos):
-        bank.add_vfo(v["mixer"], v["D"], v.get("L", 0), 0, v["gain"], 1, 1, 1, "DCC%02d" % i)
-    bank.set_dc_correction(True)
-    bank.finalize()
+    banks = []
+    for _ in range(2):
+        bank = a.Bank(fs, blk, fmt, 0)
+        for i, v in enumerate(vfos):
+            bank.add_vfo(v["mixer"], v["D"], v.get("L", 0), 0, v["gain"], 1, 1, 1, "DCC%02d" % i)
+        bank.set_dc_correction(True)
+        bank.finalize()
+        banks.append(bank)
+    bank, cut = banks
+    slice_len = 19232                                     # 601 x 32: three slices, borders inside a 1024-sample batch
+    bps = {FMT_CU8: 2, FMT_CS16: 4, FMT_CF32: 8}[fmt]
+    ptrs = [a.dev_alloc(0, slice_len * bps) for _ in range(3)]
     oracles = make_oracles(fs, blk, vfos)
     state = np.zeros(2, np.float32)
     for b in range(4):
         raw = synth_raw(fmt, b * blk, blk, seed=9, amp=0.6)
         if fmt == FMT_CF32:                              # a DC offset worth removing, on the I rail
             raw[0::2] += np.float32(0.11)
+        elif fmt == FMT_CS16:
+            raw[0::2] = np.clip(raw[0::2].astype(np.int32) + 3600, -32768, 32767).astype(np.int16)
         else:
             raw[0::2] = np.clip(raw[0::2].astype(np.int32) + 14, 0, 255).astype(np.uint8)
         x = (raw if fmt == FMT_CF32 else unpack(fmt, raw)).copy()
         dc_correct(x, state)
         bank.process(raw)
+        for i, p in enumerate(ptrs):
+            a.dev_upload(0, p, raw[2 * i * slice_len:2 * min((i + 1) * slice_len, blk)])
+        cut.submit_device_sliced(ptrs, slice_len)
+        cut.wait()
         for i, o in enumerate(oracles):
-            assert bank.output(i)[0] == o.process(x), (i, b)
+            want = o.process(x)
+            assert bank.output(i)[0] == want, (i, b)
+            assert cut.output(i)[0] == want, (i, b, "sliced")
     assert abs(float(state[0])) > 1e-4                    # the average really moved
+    for p in ptrs:
+        a.dev_free(0, p)
     bank.close()
+    cut.close()
 
 
 @pytest.mark.parametrize("fmt,slice_len", [(FMT_CF32, 96032), (FMT_CU8, 128000), (FMT_CS16, 191968)])
