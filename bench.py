@@ -428,9 +428,42 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         gloo = dist.new_group(backend="gloo")          # host-side barriers that launch nothing on the GPUs
 
+    # Host-side barrier of the step loop (peer exchange: "every rank has recorded this round's slice event"). All ranks
+    # are processes of one node, so it is a counter per rank in shared memory (a few microseconds) rather than a gloo
+    # collective (hundreds of microseconds - longer than a whole tensor-mode step at 8 GPUs). A single-process
+    # deployment (aeroddc_fleet_*) needs no barrier at all.
+    shm = shm_ctr = None
+    shm_round = [0]
+    if world > 1:
+        from multiprocessing import shared_memory
+        shm_name = "aeroddc_bench_%s" % os.environ.get("MASTER_PORT", "0")
+        if rank == 0:
+            try:
+                shared_memory.SharedMemory(name=shm_name).unlink()      # left over from a killed run
+            except FileNotFoundError:
+                pass
+            shm = shared_memory.SharedMemory(name=shm_name, create=True, size=64 * world)
+            shm.buf[:64 * world] = bytes(64 * world)
+        dist.barrier(group=gloo)
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name=shm_name)
+            try:                                                         # rank 0 owns (and unlinks) the segment
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(shm._name, "shared_memory")
+            except Exception:
+                pass
+        shm_ctr = np.ndarray((world, 8), dtype=np.int64, buffer=shm.buf)   # one cache line per rank
+        dist.barrier(group=gloo)
+
     def host_barrier():
         if world > 1:
-            dist.barrier(group=gloo)
+            shm_round[0] += 1
+            r = shm_round[0]
+            shm_ctr[rank, 0] = r
+            t_end = time.perf_counter() + 60.0
+            while int(shm_ctr[:, 0].min()) < r:
+                if time.perf_counter() > t_end:
+                    raise SystemExit("bench.py: a rank did not reach the host barrier within 60 s")
 
     # ---- bank: this rank's VFO shard (v mod world) ----
     freqs = vfo_freqs(args.vfos)
@@ -856,6 +889,11 @@ def main():
             rc = 1
     bank.close()
     if world > 1:
+        dist.barrier(group=gloo)
+        del shm_ctr
+        shm.close()
+        if rank == 0:
+            shm.unlink()
         dist.destroy_process_group()
     sys.exit(rc)
 
