@@ -669,10 +669,18 @@ constexpr int kDeepCtasPerSm = 12;     // 12 x 16 KB of ring per SM; up to 168 r
 // (which is FP32-bound) instead of displacing it.
 template <bool FAST>
 __global__ void __launch_bounds__(32, kDeepCtasPerSm) ddc_deep_kernel(const DeepParams p) {
-  extern __shared__ __align__(16) float2 ring[];   // [2][kDeepStep][32]
+  extern __shared__ __align__(128) float2 ring[];   // [2][kDeepStep][32]
   const int lane = threadIdx.x;
   Ones k1; k1.one = bcast2(p.one);
   __shared__ int s_next;
+  __shared__ __align__(8) uint64_t bars[2];
+  if (lane == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  int gdone = 0;                                           // steps this CTA has consumed so far: ring slot and barrier phase go on across items
   for (;;) {
   __syncwarp();
   if (lane == 0) s_next = atomicAdd(p.counter, 1);
@@ -718,26 +726,27 @@ __global__ void __launch_bounds__(32, kDeepCtasPerSm) ddc_deep_kernel(const Deep
   const float2* src = p.mid + (size_t)(item - range * p.ngroups) * p.n_mid * 32 + lane;
   // kDeepStep (32) input samples at a time while they last (ts and t0 are multiples of 32, so every stage starts a step
   // on its even phase): 16 / 8 / 4 outputs of deep stage 1 / 2 / 3, fully unrolled so that the filter histories are
-  // renamed rather than moved. The kernel is a stream from HBM and the bytes in flight set its speed: every lane copies
-  // its own samples one step ahead with cp.async into a two-step shared-memory ring (lane-private slots, so no barrier is
-  // needed - only the lane's own wait_group).
+  // renamed rather than moved. The kernel is a stream from HBM and the bytes in flight set its speed: the 32 rows of a
+  // step are one contiguous 8 KB run of the stream, which lane 0 fetches one step ahead with ONE bulk copy into a
+  // two-step shared-memory ring (cp.async.bulk + mbarrier; 32 per-lane cp.async per step kept the MIO queue full:
+  // mio_throttle was 45 % of this kernel's stall samples).
   int t = ts;
   const int nstep = (t1 - ts) / kDeepStep;
+  const float2* rows = src - lane;
   auto fetch = [&](int g) {
-    if (g < nstep) {
-      float2* dst = ring + ((g & 1) * kDeepStep) * 32 + lane;
-      const float2* from = src + (size_t)(ts + kDeepStep * g) * 32;
-#pragma unroll
-      for (int i = 0; i < kDeepStep; ++i)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst + i * 32)), "l"(from + i * 32) : "memory");
+    if (g < nstep && lane == 0) {
+      const int q = gdone + g;
+      mbar_expect_tx(&bars[q & 1], kDeepStep * 32 * (unsigned)sizeof(float2));
+      tma_bulk_g2s(ring + ((q & 1) * kDeepStep) * 32, rows + (size_t)(ts + kDeepStep * g) * 32, kDeepStep * 32 * (unsigned)sizeof(float2), &bars[q & 1]);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");   // an empty group keeps the count uniform
   };
   fetch(0);
   for (int g = 0; g < nstep; ++g, t += kDeepStep) {
-    fetch(g + 1);                                                  // into the slot step g-1 occupied
-    asm volatile("cp.async.wait_group 1;" ::: "memory");           // step g has landed
-    const float2* got = ring + ((g & 1) * kDeepStep) * 32 + lane;
+    const int q = gdone + g;
+    __syncwarp();                                                  // every lane is through with step g-1, whose slot the next copy overwrites
+    fetch(g + 1);
+    mbar_wait(&bars[q & 1], (unsigned)(q >> 1) & 1u);              // step g has landed
+    const float2* got = ring + ((q & 1) * kDeepStep) * 32 + lane;
     const bool keep = active && t >= t0;
     if (nd == 0) {
       if (keep) {
@@ -775,7 +784,7 @@ __global__ void __launch_bounds__(32, kDeepCtasPerSm) ddc_deep_kernel(const Deep
       if (keep) store_p2(xd + (t >> 3) + i, y2);
     }
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  gdone += nstep;
   // the last range of a stream whose length is not a multiple of 32: sample by sample
   for (; t < t1; ++t) {
     P2 x = load_p2(src + (size_t)t * 32);
