@@ -685,11 +685,15 @@ int aeroddc_bank_finalize(aeroddc_bank* b) {
   }
   CU(dmalloc((void**)&b->d_post_ctr, sizeof(int) * (1 + b->groups.size())));
   // Persistent grids of the post-processing kernels, in CTAs per SM. A flat bank overlaps block k's post-processing with
-  // block k+1's main kernel; measured on B200, a few light warps per SM beside the FP32-saturating main kernel are starved
-  // by the warp scheduler (2 + 1 CTAs per SM: the deep kernel then takes longer than the main kernel, 25 ms per step instead
-  // of 21), so both kernels take whole SMs' worth of slots for a short time instead.
+  // block k+1's main kernel. Measured on B200: too few light warps per SM beside the FP32-saturating main kernel are
+  // starved by the warp scheduler (2 + 1 per SM: the deep kernel then takes longer than the main kernel), too many take
+  // register-file slots from main-kernel CTAs for longer than their work is worth.
   const char* env_post = getenv("AERODDC_POST_CTAS");   // experiments: "deep,tail" CTAs per SM
-  int per_sm_deep = kDeepCtasPerSm, per_sm_tail = 6;
+  // Flat bank in the FP32 modes (post-processing beside the next block's main kernel): 4 + 4 per SM measured best once the
+  // deep kernel fetched by bulk copies (805 Gsps at 1024 VFOs against 788 with 12 + 6). Kernels that run alone - nested
+  // banks, whose kernels go in order, and tensor mode, whose tail cannot share an SM with the tensor kernel - take the SMs' fill.
+  const bool beside_main = !b->nested && b->mode != AERODDC_MODE_TENSOR;
+  int per_sm_deep = beside_main ? 4 : kDeepCtasPerSm, per_sm_tail = beside_main ? 4 : 6;
   if (env_post) sscanf(env_post, "%d,%d", &per_sm_deep, &per_sm_tail);
   b->post_ctas_deep = std::max(1, per_sm_deep) * b->n_sm;
   b->post_ctas_tail = std::max(1, per_sm_tail) * b->n_sm;
