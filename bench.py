@@ -875,7 +875,7 @@ def main():
         if dcc_ms is not None:
             line["dc_correction"] = {"value": float(args.vfos) * BLOCK / (dcc_ms * 1e-3) / 1e9, "unit": "Gsps", "ms_per_step": dcc_ms,
                                      "realtime_x": 250.0 / dcc_ms,
-                                     "note": "--enable-dcc: the exact sequential DC-removal recurrence (one thread per rail) runs on its own stream one block ahead of the VFO kernels"}
+                                     "note": "--enable-dcc: the exact sequential DC-removal recurrence (one lane per rail, fed and drained by two more warps through a shared-memory ring) runs on its own stream, on an SM of its own, one block ahead of the VFO kernels"}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(np.array(host[0]))
         if not args.no_side and world == 1:

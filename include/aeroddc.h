@@ -151,8 +151,10 @@ int aeroddc_bank_submit_device(aeroddc_bank *bank, const void *dev_iq, size_t n_
  * or cudaDeviceEnablePeerAccess): the main kernel's TMA tile loads then pull every tile from the GPU that holds it,
  * over NVLink, while computing - the multi-GPU exchange of the raw block fused into the
  * kernel, with no broadcast step and no staging copy; when every GPU of a node ingests 1/N of each block over its own
- * PCIe link, all N links and all N NVLink ports share the load. slice_len must be a multiple of 32 and >= 256;
- * n_slices <= 8. The kernels start after every event of ready_events[0..n_events) (cudaEvent_t, NULL entries skipped). */
+ * PCIe link, all N links and all N NVLink ports share the load. A bank in AERODDC_MODE_TENSOR, which would pull every
+ * tile across NVLink once per 64-VFO tile and outrun the links, instead lets its copy engines gather the slices into its
+ * own input buffer first (one block ahead on its copy stream; each byte crosses once) and computes from local memory.
+ * slice_len must be a multiple of 32 and >= 256; n_slices <= 8. The kernels start after every event of ready_events[0..n_events) (cudaEvent_t, NULL entries skipped). */
 int aeroddc_bank_submit_device_sliced(aeroddc_bank *bank, const void *const *slices, int n_slices, size_t slice_len,
                                       size_t n_complex, void *const *ready_events, int n_events);
 
