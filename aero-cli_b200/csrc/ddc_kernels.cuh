@@ -659,14 +659,14 @@ struct DeepParams {
   float one;
 };
 
-constexpr int kDeepStep = 32;          // input samples per unrolled step of the deep kernel; its cp.async ring holds two steps (16 KB per warp)
+constexpr int kDeepStep = 32;          // input samples per unrolled step of the deep kernel; its bulk-copy ring holds two steps (16 KB per warp)
 constexpr int kDeepWarm = 96;          // 10*(2^3 - 1) input samples reach the last deep stage's history; rounded up to a step
 constexpr int kDeepCtasPerSm = 12;     // 12 x 16 KB of ring per SM; up to 168 registers per thread
 
 // A persistent grid of one-warp CTAs takes (time range, 32-VFO group) items from a counter. The work is a stream of
-// 8 B per VFO per 32 input samples - bound by memory latency, next to nothing for the FP32 pipe - so the bank launches
-// only a couple of these warps per SM on a high-priority stream: they sit beside the following block's main kernel
-// (which is FP32-bound) instead of displacing it.
+// 8 B per VFO per input sample of this kernel - bound by memory, next to nothing for the FP32 pipe - so the bank launches
+// only a few of these warps per SM (4 beside the following block's FP32-bound main kernel, on a high-priority stream;
+// kDeepCtasPerSm when the kernel runs alone): they sit beside the main kernel instead of displacing it.
 template <bool FAST>
 __global__ void __launch_bounds__(32, kDeepCtasPerSm) ddc_deep_kernel(const DeepParams p) {
   extern __shared__ __align__(128) float2 ring[];   // [2][kDeepStep][32]

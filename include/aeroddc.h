@@ -205,7 +205,8 @@ int aeroddc_measure_fp32_peak(int device, double *tflops, double *sm_clock_mhz);
  * VFOs are sharded over the devices (flat VFO i -> device i mod N; a main VFO takes its sub-VFOs with it), each GPU
  * runs its VFO subset and returns its own payloads. The raw block reaches the GPUs in one of two ways:
  *   peer (default): GPU i uploads slice i (1/N of the block) over its own PCIe link - N concurrent H2D copies - and
- *     every bank's kernel reads all slices in place through peer memory over NVLink (aeroddc_bank_submit_device_sliced);
+ *     every bank's kernel reads all slices in place through peer memory over NVLink (aeroddc_bank_submit_device_sliced;
+ *     in AERODDC_MODE_TENSOR the bank's copy engines gather them into its own input buffer first, see there);
  *   nccl (AERODDC_EXCHANGE=nccl, or no peer access): the block is uploaded once to devices[0] and broadcast to the
  *     others with ncclBroadcast over NVLink (libnccl.so.2 is loaded at run time).
  * Same call order and error conventions as the bank; VFO indices are global (order of add_vfo).
