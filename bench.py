@@ -88,57 +88,98 @@ def parity_block(k, n=BLOCK):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock, power and throttle reasons during the timed regions (B200_PROFILING.md recipe: the values nvidia-smi
+    prints). Read through NVML every 5 ms from a thread of this process, so that a timed region of a few tens of
+    milliseconds (8 GPUs) still gets tens of samples; falls back to an `nvidia-smi -lms 50` child where NVML cannot be
+    loaded."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = [0x8, 0x40, 0x20, 0x4]      # nvmlClocksEventReason{HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.rows = []                 # (sm MHz, max MHz, W, reasons bitmask)
+        self.nvml = None
+        self.source = None
+        self.stop_flag = threading.Event()
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+            self.source = "nvml, 5 ms"
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi -lms 50"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag.is_set():
+            try:
+                self.rows.append((float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)), self.mx,
+                                  n.nvmlDeviceGetPowerUsage(self.h) / 1000.0, int(reasons(self.h))))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.005)
 
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.t.join(timeout=2)
+        elif self.proc:
+            self.proc.terminate()
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+            for ln in self.lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    row = (float(f[1]), float(f[2]), float(f[3]))
+                except ValueError:
+                    continue
+                mask = 0
+                for bit, val in zip(self.BITS, f[5:9]):
+                    if val.lower().startswith("active"):
+                        mask |= bit
+                self.rows.append(row + (mask,))
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [r[0] for r in self.rows]
+        pw = [r[2] for r in self.rows]
+        reasons = sorted(name for name, bit in zip(self.NAMES, self.BITS) if any(r[3] & bit for r in self.rows))
         # samples under load: above 60% of the maximum observed power
         thr = 0.6 * max(pw)
         load = [s for s, p in zip(sm, pw) if p >= thr] or sm
-        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "samples_under_load": len(load), "reasons": sorted(reasons)}
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(r[1] for r in self.rows)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "samples_under_load": len(load), "reasons": reasons, "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------
