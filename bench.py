@@ -478,26 +478,39 @@ def main():
     if world > 1:
         from multiprocessing import shared_memory
         shm_name = "aeroddc_bench_%s" % os.environ.get("MASTER_PORT", "0")
+        ok = [True]
         if rank == 0:
             try:
-                shared_memory.SharedMemory(name=shm_name).unlink()      # left over from a killed run
-            except FileNotFoundError:
-                pass
-            shm = shared_memory.SharedMemory(name=shm_name, create=True, size=64 * world)
-            shm.buf[:64 * world] = bytes(64 * world)
-        dist.barrier(group=gloo)
-        if rank != 0:
-            shm = shared_memory.SharedMemory(name=shm_name)
-            try:                                                         # rank 0 owns (and unlinks) the segment
-                from multiprocessing import resource_tracker
-                resource_tracker.unregister(shm._name, "shared_memory")
+                try:
+                    shared_memory.SharedMemory(name=shm_name).unlink()      # left over from a killed run
+                except FileNotFoundError:
+                    pass
+                shm = shared_memory.SharedMemory(name=shm_name, create=True, size=64 * world)
+                shm.buf[:64 * world] = bytes(64 * world)
+            except Exception as e:                                           # no usable /dev/shm: keep the gloo barrier
+                sys.stderr.write("bench.py: shared-memory barrier unavailable (%s); using gloo barriers\n" % e)
+                ok[0] = False
+        dist.broadcast_object_list(ok, src=0, group=gloo)
+        if ok[0] and rank != 0:
+            try:
+                shm = shared_memory.SharedMemory(name=shm_name)
+                try:                                                         # rank 0 owns (and unlinks) the segment
+                    from multiprocessing import resource_tracker
+                    resource_tracker.unregister(shm._name, "shared_memory")
+                except Exception:
+                    pass
             except Exception:
-                pass
-        shm_ctr = np.ndarray((world, 8), dtype=np.int64, buffer=shm.buf)   # one cache line per rank
+                shm = None
+        attached = [None] * world
+        dist.all_gather_object(attached, ok[0] and shm is not None, group=gloo)
+        if all(attached):
+            shm_ctr = np.ndarray((world, 8), dtype=np.int64, buffer=shm.buf)   # one cache line per rank
         dist.barrier(group=gloo)
 
     def host_barrier():
-        if world > 1:
+        if world > 1 and shm_ctr is None:
+            dist.barrier(group=gloo)
+        elif world > 1:
             shm_round[0] += 1
             r = shm_round[0]
             shm_ctr[rank, 0] = r
@@ -931,10 +944,14 @@ def main():
     bank.close()
     if world > 1:
         dist.barrier(group=gloo)
-        del shm_ctr
-        shm.close()
-        if rank == 0:
-            shm.unlink()
+        shm_ctr = None
+        if shm is not None:
+            try:
+                shm.close()
+                if rank == 0:
+                    shm.unlink()
+            except Exception:
+                pass
         dist.destroy_process_group()
     sys.exit(rc)
 
