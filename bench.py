@@ -882,6 +882,9 @@ def main():
                 "algorithmic_flop_per_vfo_sample": FLOPS_MAIN,
                 "issue_bound_note": "the reference's arithmetic is un-fused (1 flop per lane-op; only the half-band centre tap 0.5 fuses exactly) plus a 14 lane-op exact NCO step: "
                                     "100%% FP32-pipe use = %.1f%% of the FMA peak" % (100 * FLOPS_MAIN / (2 * 37.4)),
+                # the same launch against the FP32 pipe's lane-op rate (half the FMA-flop peak): 37.4 pipe cycles per
+                # VFO-sample (SASS count) x VFO-samples per launch / launch time
+                "fp32_pipe_use": (37.4 / FLOPS_MAIN) * achieved / (peak_tflops / 2.0),
                 "hbm": {"achieved_gbs": alg_bytes / (mm * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                         "frac": (alg_bytes / (mm * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None},
             },
