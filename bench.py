@@ -879,6 +879,8 @@ def main():
                 "frac": achieved / peak_tflops, "traffic": traffic,
                 "peak_source": "FFMA2 issue probe measured in this run (aeroddc_measure_fp32_peak, FMA = 2 flop); MEASURED_PEAKS.json carries no FP32 figure",
                 "launch_ms": mm, "share_of_step": mm / (dev_ms / args.steps),
+                "share_note": "block k's deep and tail kernels run on their own stream beside block k+1's main kernel, so a main-kernel launch spans almost "
+                              "the whole pipelined step; serialised under ncu (profiles/r2_launches_bench.csv) it is 18.5 of 19.9 ms = 93 % of a step's kernel time",
                 "algorithmic_flop_per_vfo_sample": FLOPS_MAIN,
                 "issue_bound_note": "the reference's arithmetic is un-fused (1 flop per lane-op; only the half-band centre tap 0.5 fuses exactly) plus a 14 lane-op exact NCO step: "
                                     "100%% FP32-pipe use = %.1f%% of the FMA peak" % (100 * FLOPS_MAIN / (2 * 37.4)),
